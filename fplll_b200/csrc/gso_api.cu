@@ -1,0 +1,736 @@
+// gso_api.cu — kernels + extern "C" entry points declared in include/b200gso.h.
+//
+// Launch geometry: one warp per lattice, WARPS_PER_CTA lattices per CTA, grid = ceil(batch / WARPS_PER_CTA).
+// With the panel-packed layout (gso_layout.cuh) every hot global access is a 256-byte coalesced warp load, so the
+// kernels are HBM-streaming: occupancy (16+ resident warps per SM, 8 independent loads in flight per lane in the
+// sweep loops) is what hides DRAM latency, not shared-memory tiling.  There is no CPU fallback anywhere.
+#include "../../include/b200gso.h"
+#include "gso_lll.cuh"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+thread_local std::string g_err;
+
+#define CK(call)                                                                                   \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+    {                                                                                              \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+      return B200GSO_ECUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+__device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *&lov, int &lane)
+{
+  extern __shared__ __align__(16) double smem[];
+  const int w = threadIdx.x >> 5;
+  lane        = threadIdx.x & 31;
+  const int l = blockIdx.x * (blockDim.x >> 5) + w;
+  const size_t per = WarpSmem::doubles(S.d, S.n) + (size_t)((S.d + 2 + 1) & ~1);
+  s.carve(smem + (size_t)w * per, S.d, S.n);
+  lov = smem + (size_t)w * per + WarpSmem::doubles(S.d, S.n);
+  if (l >= S.B)
+    return false;
+  v = S.view(l);
+  return true;
+}
+
+// size_increased(), gso.cpp:368-403: init_row_size, zero-filled bf, update_bf for every row; fresh metadata.
+__global__ void k_init(Batch S)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  if (lane < M_STRIDE)
+    v.meta[lane] = 0;
+  const size_t nbf = bf_size(v.d, v.n);
+  for (size_t t = lane; t < nbf; t += 32)
+    v.bf[t] = 0.0;
+  __syncwarp();
+  for (int i = 0; i < v.d; i++)
+  {
+    const int nz = size_nz_warp(v.b + (size_t)i * v.ldb, v.n, lane);
+    if (lane == 0)
+    {
+      v.irs[i]      = max(nz, 1);
+      v.valid[i]    = 0;
+      v.row_expo[i] = 0;
+    }
+    __syncwarp();
+    warp_update_bf(v, i, lane);
+  }
+}
+
+// repack a plain row-major batch*d*n int64 buffer into the ldb-strided device basis
+__global__ void k_pack_b(Batch S, const int64_t *src)
+{
+  const int l = blockIdx.y;
+  View v      = S.view(l);
+  const size_t tot = (size_t)S.d * S.n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x)
+  {
+    const int i = (int)(t / S.n), c = (int)(t % S.n);
+    v.b[(size_t)i * S.ldb + c] = src[(size_t)l * tot + t];
+  }
+}
+__global__ void k_unpack_b(Batch S, int64_t *dst)
+{
+  const int l = blockIdx.y;
+  View v      = S.view(l);
+  const size_t tot = (size_t)S.d * S.n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x)
+  {
+    const int i = (int)(t / S.n), c = (int)(t % S.n);
+    dst[(size_t)l * tot + t] = v.b[(size_t)i * S.ldb + c];
+  }
+}
+
+__global__ void k_discover_all(Batch S)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  while (v.meta[M_NKR] < v.d)
+    warp_discover_row(v, lane);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_update_row(Batch S, int i, int last_j, int *ok)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const bool r = warp_update_gso_row(v, i, last_j, s, lane);
+  if (ok && lane == 0)
+    ok[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = r ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_update_gso(Batch S, int *ok)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  bool r = true;
+  for (int i = 0; i < v.d && r; i++)
+    r = warp_update_gso_row(v, i, i, s, lane);
+  if (ok && lane == 0)
+    ok[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = r ? 1 : 0;
+}
+
+__global__ void k_row_addmul_we(Batch S, int i, int j, const double *x, const long *expo_add)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  warp_row_addmul_we(v, i, j, x[l], expo_add ? expo_add[l] : 0, lane);
+}
+
+__global__ void k_row_op_end(Batch S, int first, int last)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  warp_row_op_end(v, first, last, lane);
+}
+
+// invalidate_gso_row(i, 0) only (gso_interface.cpp:24-30) — used by the g=0 timing mode
+__global__ void k_invalidate_gso_row(Batch S, int i)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < S.B)
+    S.view(l).valid[i] = 0;
+}
+
+__global__ void k_row_swap(Batch S, int i, int j)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  warp_row_swap(v, i, j, lane);
+}
+
+__global__ void k_move_row(Batch S, int old_r, int new_r)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  warp_move_row(v, old_r, new_r, lane);
+}
+
+__global__ void k_set_r(Batch S, int i, int j, const double *f)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < S.B)
+  {
+    View v              = S.view(l);
+    v.r[tri_off(i) + j] = f[l];
+    if (v.valid[i] == j)
+      v.valid[i] = j + 1;
+  }
+}
+
+__global__ void k_upload_row(Batch S, int i, const int64_t *rows)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = lane; c < v.n; c += 32)
+    v.b[(size_t)i * v.ldb + c] = rows[(size_t)l * v.n + c];
+  __syncwarp();
+  warp_row_op_end(v, i, i + 1, lane);
+}
+
+// dense read-back (the reference's Matrix<FT> view of the state)
+__global__ void k_unpack_state(Batch S, double *mu, double *r, double *gf, double *bf)
+{
+  const int l = blockIdx.y;
+  View v      = S.view(l);
+  const int d = S.d, n = S.n;
+  const size_t dd = (size_t)d * d, dn = (size_t)d * n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < dd; t += (size_t)gridDim.x * blockDim.x)
+  {
+    const int i = (int)(t / d), j = (int)(t % d);
+    if (mu)
+      mu[l * dd + t] = (j < i) ? v.mu[mu_off(i, j)] : 0.0;
+    if (r)
+      r[l * dd + t] = (j <= i) ? v.r[tri_off(i) + j] : 0.0;
+    if (gf)
+      gf[l * dd + t] = (j <= i) ? v.gf[tri_off(i) + j] : 0.0;
+  }
+  if (bf)
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < dn; t += (size_t)gridDim.x * blockDim.x)
+    {
+      const int i = (int)(t / n), c = (int)(t % n);
+      bf[l * dn + t] = v.bf[bf_off(i, c, n)];
+    }
+}
+
+__global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row)
+{
+  const int l = blockIdx.x;
+  View v      = S.view(l);
+  for (int j = threadIdx.x; j < S.d; j += blockDim.x)
+  {
+    if (mu_row)
+      mu_row[(size_t)l * S.d + j] = (j < i) ? v.mu[mu_off(i, j)] : 0.0;
+    if (r_row)
+      r_row[(size_t)l * S.d + j] = (j <= i) ? v.r[tri_off(i) + j] : 0.0;
+  }
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_lll(Batch S, double delta, double eta, int *status, long *stats)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  LLLStats st;
+  const int r = warp_lll<MAXQ>(v, s, lov, delta, eta, lane, st);
+  if (lane == 0)
+  {
+    status[l] = r;
+    if (stats)
+    {
+      stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
+      stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
+    }
+  }
+}
+
+}  // namespace
+
+struct b200gso
+{
+  Batch S;
+  int device;
+  cudaStream_t stream;
+  size_t smem_bytes;
+  int *d_ok;      // batch ints
+  double *d_tmp;  // batch doubles
+  long *d_ltmp;   // batch longs
+  std::vector<void *> allocs;
+};
+
+static int grid_warps(const b200gso *h) { return (h->S.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+
+template <class T> static int dev_alloc(b200gso *h, T **p, size_t count)
+{
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess)
+  {
+    g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return B200GSO_ENOMEM;
+  }
+  h->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+extern "C" {
+
+const char *b200gso_version(void) { return "b200gso 0.1 (sm_100a)"; }
+const char *b200gso_last_error(void) { return g_err.c_str(); }
+
+int b200gso_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int device)
+{
+  if (!out || batch <= 0 || d <= 0 || n <= 0 || (flags & 1))
+  {
+    g_err = "b200gso_create: bad arguments (GSO_INT_GRAM is not supported on the device)";
+    return B200GSO_EINVAL;
+  }
+  if (b200gso_device_count() <= device)
+  {
+    g_err = "b200gso_create: no CUDA device (this library has no CPU fallback)";
+    return B200GSO_ENODEV;
+  }
+  CK(cudaSetDevice(device));
+  b200gso *h = new b200gso();
+  h->device  = device;
+  Batch &S   = h->S;
+  S.B = batch, S.d = d, S.n = n, S.ldb = ld_b(n), S.row_expo_en = (flags & B200GSO_ROW_EXPO) ? 1 : 0;
+  S.b_stride       = (size_t)d * S.ldb;
+  S.bf_stride      = bf_size(d, n);
+  S.mu_stride      = mu_size(d);
+  S.tri_stride     = tri_size(d);
+  S.scratch_stride = tri_size(d);
+  int rc = 0;
+  rc |= dev_alloc(h, &S.b, S.b_stride * batch);
+  rc |= dev_alloc(h, &S.bf, S.bf_stride * batch);
+  rc |= dev_alloc(h, &S.mu, S.mu_stride * batch);
+  rc |= dev_alloc(h, &S.r, S.tri_stride * batch);
+  rc |= dev_alloc(h, &S.gf, S.tri_stride * batch);
+  rc |= dev_alloc(h, &S.scratch, S.scratch_stride * batch);
+  rc |= dev_alloc(h, &S.row_expo, (size_t)d * batch);
+  rc |= dev_alloc(h, &S.valid, (size_t)d * batch);
+  rc |= dev_alloc(h, &S.irs, (size_t)d * batch);
+  rc |= dev_alloc(h, &S.meta, (size_t)M_STRIDE * batch);
+  rc |= dev_alloc(h, &h->d_ok, (size_t)batch);
+  rc |= dev_alloc(h, &h->d_tmp, (size_t)batch);
+  rc |= dev_alloc(h, &h->d_ltmp, (size_t)batch * 4);
+  if (rc)
+  {
+    for (void *p : h->allocs)
+      cudaFree(p);
+    delete h;
+    return B200GSO_ENOMEM;
+  }
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->smem_bytes = WARPS_PER_CTA * (WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1)) * sizeof(double);
+  if (h->smem_bytes > 227 * 1024)
+  {
+    g_err = "b200gso_create: d/n too large for the per-warp shared-memory scratch";
+    b200gso_destroy(h);
+    return B200GSO_EINVAL;
+  }
+  const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row,
+                       (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
+                       (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
+                       (const void *)k_lll<4>,       (const void *)k_lll<8>,       (const void *)k_lll<16>};
+  for (const void *f : fns)
+    CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
+  CK(cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(S.gf, 0, S.tri_stride * batch * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(S.meta, 0, (size_t)M_STRIDE * batch * sizeof(int), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+void b200gso_destroy(b200gso_t *h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->device);
+  if (h->stream)
+  {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (void *p : h->allocs)
+    cudaFree(p);
+  delete h;
+}
+
+int b200gso_set_basis_dev(b200gso_t *h, const int64_t *dev_b)
+{
+  if (!h || !dev_b)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  dim3 g(64, h->S.B);
+  k_pack_b<<<g, 256, 0, h->stream>>>(h->S, dev_b);
+  k_init<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_set_basis(b200gso_t *h, const int64_t *b)
+{
+  if (!h || !b)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->S.B * h->S.d * h->S.n;
+  int64_t *tmp     = nullptr;
+  CK(cudaMalloc(&tmp, cnt * sizeof(int64_t)));
+  cudaError_t e = cudaMemcpyAsync(tmp, b, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
+  int rc        = (e == cudaSuccess) ? b200gso_set_basis_dev(h, tmp) : B200GSO_ECUDA;
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess)
+    g_err = cudaGetErrorString(e);
+  return rc;
+}
+
+int b200gso_get_basis(b200gso_t *h, int64_t *b)
+{
+  if (!h || !b)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->S.B * h->S.d * h->S.n;
+  int64_t *tmp     = nullptr;
+  CK(cudaMalloc(&tmp, cnt * sizeof(int64_t)));
+  dim3 g(64, h->S.B);
+  k_unpack_b<<<g, 256, 0, h->stream>>>(h->S, tmp);
+  cudaError_t e = cudaMemcpyAsync(b, tmp, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess)
+  {
+    g_err = cudaGetErrorString(e);
+    return B200GSO_ECUDA;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_upload_row(b200gso_t *h, int i, const int64_t *rows)
+{
+  if (!h || !rows || i < 0 || i >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->S.B * h->S.n;
+  int64_t *tmp     = nullptr;
+  CK(cudaMallocAsync(&tmp, cnt * sizeof(int64_t), h->stream));
+  CK(cudaMemcpyAsync(tmp, rows, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  k_upload_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, tmp);
+  CK(cudaFreeAsync(tmp, h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_discover_all_rows(b200gso_t *h)
+{
+  if (!h)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int fetch_ok(b200gso_t *h, int *ok)
+{
+  if (ok)
+  {
+    CK(cudaMemcpyAsync(ok, h->d_ok, sizeof(int) * h->S.B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_update_gso_row(b200gso_t *h, int i, int last_j, int *ok)
+{
+  if (!h || i < 0 || i >= h->S.d || last_j < 0 || last_j > i)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_update_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, last_j, h->d_ok);
+  return fetch_ok(h, ok);
+}
+
+int b200gso_update_gso(b200gso_t *h, int *ok)
+{
+  if (!h)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, h->d_ok);
+  return fetch_ok(h, ok);
+}
+
+int b200gso_row_addmul_we(b200gso_t *h, int i, int j, const double *x, const long *expo_add)
+{
+  if (!h || !x || i < 0 || j < 0 || i >= h->S.d || j >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_tmp, x, sizeof(double) * h->S.B, cudaMemcpyHostToDevice, h->stream));
+  if (expo_add)
+    CK(cudaMemcpyAsync(h->d_ltmp, expo_add, sizeof(long) * h->S.B, cudaMemcpyHostToDevice, h->stream));
+  k_row_addmul_we<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, j, h->d_tmp,
+                                                                                   expo_add ? h->d_ltmp : nullptr);
+  CK(cudaStreamSynchronize(h->stream));  // host arrays may be reused by the caller
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_row_op_begin(b200gso_t *h, int first, int last)
+{
+  (void)first, (void)last;  // no-op in release builds of the reference too (gso_interface.h:785-788)
+  return h ? 0 : B200GSO_EINVAL;
+}
+
+int b200gso_row_op_end(b200gso_t *h, int first, int last)
+{
+  if (!h || first < 0 || last > h->S.d || first > last)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_row_op_end<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, first, last);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_row_swap(b200gso_t *h, int i, int j)
+{
+  if (!h || i < 0 || j < 0 || i >= h->S.d || j >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_row_swap<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, j);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_move_row(b200gso_t *h, int old_r, int new_r)
+{
+  if (!h || old_r < 0 || new_r < 0 || old_r >= h->S.d || new_r >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_move_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, old_r, new_r);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_set_r(b200gso_t *h, int i, int j, const double *f)
+{
+  if (!h || !f || i < 0 || i >= h->S.d || j < 0 || j > i)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_tmp, f, sizeof(double) * h->S.B, cudaMemcpyHostToDevice, h->stream));
+  k_set_r<<<(h->S.B + 127) / 128, 128, 0, h->stream>>>(h->S, i, j, h->d_tmp);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_get_state(b200gso_t *h, double *mu, double *r, double *gf, double *bf, int64_t *row_expo,
+                      int *gso_valid_cols, int *init_row_size, int *meta)
+{
+  if (!h)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const Batch &S  = h->S;
+  const size_t dd = (size_t)S.B * S.d * S.d, dn = (size_t)S.B * S.d * S.n;
+  double *t_mu = nullptr, *t_r = nullptr, *t_gf = nullptr, *t_bf = nullptr;
+  if (mu)
+    CK(cudaMalloc(&t_mu, dd * 8));
+  if (r)
+    CK(cudaMalloc(&t_r, dd * 8));
+  if (gf)
+    CK(cudaMalloc(&t_gf, dd * 8));
+  if (bf)
+    CK(cudaMalloc(&t_bf, dn * 8));
+  dim3 g(32, S.B);
+  k_unpack_state<<<g, 256, 0, h->stream>>>(S, t_mu, t_r, t_gf, t_bf);
+  if (mu)
+    cudaMemcpyAsync(mu, t_mu, dd * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (r)
+    cudaMemcpyAsync(r, t_r, dd * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (gf)
+    cudaMemcpyAsync(gf, t_gf, dd * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (bf)
+    cudaMemcpyAsync(bf, t_bf, dn * 8, cudaMemcpyDeviceToHost, h->stream);
+  std::vector<int> tmp;
+  if (row_expo)
+  {
+    tmp.resize((size_t)S.B * S.d);
+    cudaMemcpyAsync(tmp.data(), S.row_expo, tmp.size() * 4, cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (gso_valid_cols)
+    cudaMemcpyAsync(gso_valid_cols, S.valid, (size_t)S.B * S.d * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (init_row_size)
+    cudaMemcpyAsync(init_row_size, S.irs, (size_t)S.B * S.d * 4, cudaMemcpyDeviceToHost, h->stream);
+  std::vector<int> m;
+  if (meta)
+  {
+    m.resize((size_t)S.B * M_STRIDE);
+    cudaMemcpyAsync(m.data(), S.meta, m.size() * 4, cudaMemcpyDeviceToHost, h->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(t_mu), cudaFree(t_r), cudaFree(t_gf), cudaFree(t_bf);
+  if (e != cudaSuccess)
+  {
+    g_err = cudaGetErrorString(e);
+    return B200GSO_ECUDA;
+  }
+  if (row_expo)
+    for (size_t t = 0; t < tmp.size(); t++)
+      row_expo[t] = tmp[t];
+  if (meta)
+    for (int l = 0; l < S.B; l++)
+      for (int q = 0; q < 4; q++)
+        meta[4 * l + q] = m[(size_t)l * M_STRIDE + q];
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_get_mu_r_row(b200gso_t *h, int i, double *mu_row, double *r_row, int *valid)
+{
+  if (!h || i < 0 || i >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const Batch &S   = h->S;
+  const size_t cnt = (size_t)S.B * S.d;
+  double *t        = nullptr;
+  CK(cudaMallocAsync(&t, 2 * cnt * 8, h->stream));
+  k_get_row<<<S.B, 128, 0, h->stream>>>(S, i, mu_row ? t : nullptr, r_row ? t + cnt : nullptr);
+  if (mu_row)
+    CK(cudaMemcpyAsync(mu_row, t, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (r_row)
+    CK(cudaMemcpyAsync(r_row, t + cnt, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (valid)
+    CK(cudaMemcpy2DAsync(valid, sizeof(int), S.valid + i, (size_t)S.d * sizeof(int), sizeof(int), S.B,
+                         cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaFreeAsync(t, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats)
+{
+  if (!h || !status)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const Batch &S = h->S;
+  if (S.d > 512)
+  {
+    g_err = "b200gso_lll: d > 512 not supported by the warp-resident Babai registers";
+    return B200GSO_EINVAL;
+  }
+  int *d_st = nullptr;
+  long *d_stats = nullptr;
+  CK(cudaMallocAsync(&d_st, sizeof(int) * S.B, h->stream));
+  CK(cudaMallocAsync(&d_stats, sizeof(long) * 4 * S.B, h->stream));
+  const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
+  if (S.d <= 128)
+    k_lll<4><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+  else if (S.d <= 256)
+    k_lll<8><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+  else
+    k_lll<16><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+  CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
+  if (stats)
+    CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaFreeAsync(d_st, h->stream));
+  CK(cudaFreeAsync(d_stats, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_per_launch)
+{
+  if (!h || !ms_per_launch || reps <= 0 || i < 0 || i >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+  for (auto &e : ev)
+    CK(cudaEventCreate(&e));
+  for (int r = 0; r < reps; r++)
+  {
+    if (invalidate)
+      k_row_op_end<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, i + 1);
+    else
+      k_invalidate_gso_row<<<(h->S.B + 127) / 128, 128, 0, h->stream>>>(h->S, i);
+    CK(cudaEventRecord(ev[2 * r], h->stream));
+    k_update_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, i, h->d_ok);
+    CK(cudaEventRecord(ev[2 * r + 1], h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  double tot = 0;
+  for (int r = 0; r < reps; r++)
+  {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]));
+    tot += ms;
+  }
+  for (auto &e : ev)
+    cudaEventDestroy(e);
+  *ms_per_launch = (float)(tot / reps);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_sync(b200gso_t *h)
+{
+  if (!h)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,502 @@
+// gso_warp.cuh — warp-cooperative device implementation of the MatGSO<long,double> state machine.
+//
+// One warp owns one lattice.  Every routine is the reference routine named in its comment with the SAME
+// per-accumulator operation order (separately rounded multiply then add/sub, ascending index), so results are
+// bit-identical to the reference's fp64 GSO — see SURVEY.md §0.8 / §7 "order-preserving schedules".
+// All 32 lanes must call these functions together (they contain __syncwarp / shuffles).
+#pragma once
+#include "gso_layout.cuh"
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace b200 {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// per-warp shared-memory scratch (doubles): vb[n] | rrow[dpad] | murow[dpad] | aux[dpad] | xs[dpad]
+struct WarpSmem
+{
+  double *vb, *rrow, *murow, *aux, *xs;
+  __host__ __device__ static size_t doubles(int d, int n)
+  {
+    int dpad = (d + 32 + 1) & ~1, npad = (n + 1) & ~1;
+    return (size_t)npad + 4 * (size_t)dpad;
+  }
+  __device__ void carve(double *base, int d, int n)
+  {
+    int dpad = (d + 32 + 1) & ~1, npad = (n + 1) & ~1;
+    vb = base, rrow = vb + npad, murow = rrow + dpad, aux = murow + dpad, xs = aux + dpad;
+  }
+};
+
+// FP_NR<double>::exponent, nr_FP_d.inl:44
+__device__ inline long fexponent(double x) { return (long)ilogb(x) + 1; }
+
+// FP_NR<double>::get_si_exp_we, nr_FP_d.inl:46-53
+__device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
+{
+  if (x == 0)
+    expo = 0;
+  else
+  {
+    long e = fexponent(x) + expo_add - 63;
+    expo   = e > 0 ? e : 0;
+  }
+  return (long)ldexp(x, (int)(expo_add - expo));
+}
+
+// FP_NR<double>::rnd_we, nr_FP_d.inl:226-233 (rint = round-half-even)
+__device__ inline double rnd_we(double x, long expo_add)
+{
+  if (fexponent(x) + expo_add >= 53)
+    return x;
+  return ldexp(rint(ldexp(x, (int)expo_add)), (int)-expo_add);
+}
+
+// MatGSO::update_bf(i), gso.cpp:24-48 for Z_NR<long> (get_f_exp = frexp((double)x), nr_Z_misc.inl:17-22)
+__device__ inline void warp_update_bf(const View &v, int i, int lane)
+{
+  const int n = max(v.meta[M_NKC], v.irs[i]);
+  const int64_t *brow = v.b + (size_t)i * v.ldb;
+  if (v.row_expo_en)
+  {
+    int mx = INT_MIN;
+    for (int c = lane; c < n; c += 32)
+    {
+      int e;
+      (void)frexp((double)brow[c], &e);
+      mx = max(mx, e);
+    }
+    for (int o = 16; o; o >>= 1)
+      mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    for (int c = lane; c < n; c += 32)
+    {
+      int e;
+      double f               = frexp((double)brow[c], &e);
+      v.bf[bf_off(i, c, v.n)] = ldexp(f, e - mx);
+    }
+    if (lane == 0)
+      v.row_expo[i] = mx;
+  }
+  else
+  {
+    for (int c = lane; c < n; c += 32)
+      v.bf[bf_off(i, c, v.n)] = (double)brow[c];
+  }
+  __syncwarp();
+}
+
+// invalidate_gram_row, gso.cpp:50-54
+__device__ inline void warp_invalidate_gram_row(const View &v, int i, int lane)
+{
+  double *g = v.gf + tri_off(i);
+  for (int j = lane; j <= i; j += 32)
+    g[j] = CUDART_NAN;
+}
+
+// discover_row, gso.cpp:56-82 (float Gram)
+__device__ inline void warp_discover_row(const View &v, int lane)
+{
+  const int i = v.meta[M_NKR];
+  __syncwarp();
+  if (lane == 0)
+  {
+    v.meta[M_NKR] = i + 1;
+    if (!v.meta[M_LOCKED])
+    {
+      v.meta[M_NSR] = i + 1;
+      v.meta[M_NKC] = max(v.meta[M_NKC], v.irs[i]);
+    }
+    v.valid[i] = 0;
+  }
+  warp_invalidate_gram_row(v, i, lane);
+  __syncwarp();
+}
+
+// Sequential dot product of rows i and j of bf over [0,ncols) — numvect.h:385-395 — executed redundantly by the
+// lanes that need it (each lane its own j).  vb = bf_i staged in shared memory.
+__device__ inline double lane_dot(const double *__restrict__ bfcol /* &bf(j,0) */, const double *vb, int ncols)
+{
+  double acc = __dmul_rn(bfcol[0], vb[0]);
+  int c      = 1;
+  for (; c + 8 <= ncols; c += 8)
+  {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      x[u] = bfcol[(size_t)(c + u) * 32];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      acc = __dadd_rn(acc, __dmul_rn(x[u], vb[c + u]));
+  }
+  for (; c < ncols; c++)
+    acc = __dadd_rn(acc, __dmul_rn(bfcol[(size_t)c * 32], vb[c]));
+  return acc;
+}
+
+// MatGSOInterface::update_gso_row(i, last_j), gso_interface.cpp:131-164, with get_gram (gso.h:314-331) inlined.
+// Lane l of panel p owns column j = 32p + l of row i:
+//   acc_j = g(i,j);  for k = 0..j-1 (ascending): acc_j -= mu(j,k) * r(i,k)      [two roundings per step]
+// r(i,k) for k outside the panel comes from shared memory (rrow), inside the panel by shuffle from the lane that
+// has just finished its own chain — the "right-looking" schedule that keeps every chain in reference order.
+// Returns false (warp-uniform) if some mu(i,j) is not finite; gso_valid_cols[i] is then left unchanged.
+__device__ inline bool warp_update_gso_row(const View &v, int i, int last_j, WarpSmem &s, int lane)
+{
+  if (i >= v.meta[M_NKR])
+    warp_discover_row(v, lane);
+  const int j0 = max(0, v.valid[i]);
+  if (j0 > last_j)
+    return true;
+  const int ncols = v.meta[M_NKC], n = v.n;
+  double *gfrow = v.gf + tri_off(i), *rrow_g = v.r + tri_off(i);
+
+  int anyn = 0;
+  for (int j = j0 + lane; j <= last_j; j += 32)
+    anyn |= (gfrow[j] != gfrow[j]);
+  anyn = __any_sync(FULL, anyn);
+  if (anyn)
+    for (int c = lane; c < ncols; c += 32)
+      s.vb[c] = v.bf[bf_off(i, c, n)];
+  for (int k = lane; k < j0; k += 32)
+    s.rrow[k] = rrow_g[k];
+  __syncwarp();
+
+  bool ok      = true;
+  const int jl = min(last_j, i - 1);  // last off-diagonal column to produce
+  for (int p = j0 >> 5; 32 * p <= jl; ++p)
+  {
+    const int j     = 32 * p + lane;
+    const bool act  = (j >= j0) && (j <= jl);
+    double acc      = 0.0;
+    if (act)
+    {
+      double g = gfrow[j];
+      if (g != g)
+      {
+        g        = lane_dot(v.bf + bf_off(j, 0, n), s.vb, ncols);
+        gfrow[j] = g;
+      }
+      acc = g;
+    }
+    else if (j < j0)
+      acc = s.rrow[j];  // already-valid r(i,j): only broadcast in the triangle below
+    const double *mup = v.mu + mu_panel_base(p) + lane;
+    // rectangular part: columns k < 32p, all r(i,k) already in shared memory
+    if (act)
+    {
+      const int kend = 32 * p;
+      int k          = 0;
+      for (; k + 8 <= kend; k += 8)
+      {
+        double m[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          m[u] = mup[(size_t)(k + u) * 32];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          acc = __dsub_rn(acc, __dmul_rn(m[u], s.rrow[k + u]));
+      }
+    }
+    // triangular part: column 32p+t is final in lane t once steps 0..t-1 are applied
+    {
+      double m[32];
+      const bool ld = act;
+#pragma unroll
+      for (int t = 0; t < 32; t++)
+        m[t] = (ld && lane > t) ? mup[(size_t)(32 * p + t) * 32] : 0.0;
+#pragma unroll
+      for (int t = 0; t < 31; t++)
+      {
+        const double rk = __shfl_sync(FULL, acc, t);
+        if (act && lane > t)
+          acc = __dsub_rn(acc, __dmul_rn(m[t], rk));
+      }
+    }
+    if (act)
+    {
+      rrow_g[j]       = acc;
+      s.rrow[j]       = acc;
+      const double rd = v.r[tri_off(j) + j];
+      const double mm = __ddiv_rn(acc, rd);
+      v.mu[mu_off(i, j)] = mm;
+      s.murow[j]      = mm;
+      if (!isfinite(mm))
+        ok = false;
+    }
+    __syncwarp();
+  }
+  ok = __all_sync(FULL, ok);
+  if (!ok)
+    return false;
+
+  if (last_j >= i)
+  {
+    // diagonal r(i,i) = g(i,i) - sum_{k<i} mu(i,k) r(i,k): products in parallel, one ordered subtraction chain
+    for (int k = lane; k < min(j0, i); k += 32)
+      s.murow[k] = v.mu[mu_off(i, k)];
+    __syncwarp();
+    for (int k = lane; k < i; k += 32)
+      s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
+    __syncwarp();
+    if (lane == 0)
+    {
+      double g = gfrow[i];
+      if (g != g)
+      {
+        if (!anyn)  // vb not staged (cannot happen: gf(i,i) NaN implies anyn) — keep for safety
+          for (int c = 0; c < ncols; c++)
+            s.vb[c] = v.bf[bf_off(i, c, n)];
+        g = __dmul_rn(s.vb[0], s.vb[0]);
+        for (int c = 1; c < ncols; c++)
+          g = __dadd_rn(g, __dmul_rn(s.vb[c], s.vb[c]));
+        gfrow[i] = g;
+      }
+      double acc = g;
+      for (int k = 0; k < i; k++)
+        acc = __dsub_rn(acc, s.aux[k]);
+      rrow_g[i] = acc;
+    }
+    __syncwarp();
+  }
+  if (lane == 0)
+    v.valid[i] = last_j + 1;
+  __syncwarp();
+  return true;
+}
+
+// row_op_end(first,last), gso_interface.cpp:32-53
+__device__ inline void warp_row_op_end(const View &v, int first, int last, int lane)
+{
+  const int nkr = v.meta[M_NKR];
+  for (int i = first; i < last; i++)
+  {
+    warp_update_bf(v, i, lane);
+    warp_invalidate_gram_row(v, i, lane);
+    for (int j = i + 1 + lane; j < nkr; j += 32)
+      v.gf[tri_off(j) + i] = CUDART_NAN;
+    if (lane == 0)
+      v.valid[i] = 0;
+  }
+  for (int i = last + lane; i < nkr; i += 32)
+    v.valid[i] = min(v.valid[i], first);
+  __syncwarp();
+}
+
+// row_addmul_we(i, j, x, expo_add), gso.cpp:236-262 -> row_add/row_sub/row_addmul_si/row_addmul_si_2exp
+// (gso.cpp:84-195, numvect.h:268-341) on b only (u, u_inv_t empty in the BKZ regime).  int64 wraps like Z_NR<long>.
+__device__ inline void warp_row_addmul_we(const View &v, int i, int j, double x, long expo_add, int lane)
+{
+  long expo;
+  const long lx = get_si_exp_we(x, expo, expo_add);
+  if (expo == 0 && lx == 0)
+    return;
+  const int nc           = v.meta[M_NKC];
+  unsigned long long *bi = (unsigned long long *)(v.b + (size_t)i * v.ldb);
+  const unsigned long long *bj = (const unsigned long long *)(v.b + (size_t)j * v.ldb);
+  const unsigned long long ux  = (unsigned long long)lx;
+  if (expo == 0)
+    for (int c = lane; c < nc; c += 32)
+      bi[c] += bj[c] * ux;
+  else
+    for (int c = lane; c < nc; c += 32)
+    {
+      unsigned long long t = bj[c] * ux;
+      bi[c] += (expo >= 64 ? 0ull : (t << expo));
+    }
+  __syncwarp();
+}
+
+// row_swap(i,j), gso.cpp:264-287: integer rows only
+__device__ inline void warp_row_swap(const View &v, int i, int j, int lane)
+{
+  int64_t *a = v.b + (size_t)i * v.ldb, *b = v.b + (size_t)j * v.ldb;
+  for (int c = lane; c < v.n; c += 32)
+  {
+    int64_t t = a[c];
+    a[c]      = b[c];
+    b[c]      = t;
+  }
+  __syncwarp();
+}
+
+__device__ inline int size_nz_warp(const int64_t *row, int n, int lane)
+{
+  int last = 0;
+  for (int c = lane; c < n; c += 32)
+    if (row[c] != 0)
+      last = c + 1;
+  for (int o = 16; o; o >>= 1)
+    last = max(last, __shfl_xor_sync(FULL, last, o));
+  return last;
+}
+
+// move_row(old_r, new_r), gso.cpp:289-366 (float Gram, no transforms).  Rotations of mu, r, b, bf, row_expo,
+// gso_valid_cols are done column-by-column (each lane carries one column through the rotated rows, no scratch);
+// only the entries that can still be valid after the call (columns < min(old,new)) are moved
+// for mu and r.  The symmetric row+column rotation of gf (matrix.cpp:65-93) goes through v.scratch.
+__device__ inline void warp_move_row(const View &v, int old_r, int new_r, int lane)
+{
+  if (old_r == new_r)
+    return;
+  const int nkr   = v.meta[M_NKR];
+  const bool right = new_r < old_r;  // rows [lo..hi]: right: row hi -> lo; left: row lo -> hi
+  const int lo = right ? new_r : old_r, hi = right ? old_r : new_r;
+  for (int i = lo + lane; i < nkr; i += 32)
+    v.valid[i] = min(v.valid[i], lo);
+  __syncwarp();
+  // mu (columns k < lo) — panel layout
+  for (int k = lane; k < lo; k += 32)
+  {
+    if (right)
+    {
+      double t = v.mu[mu_off(hi, k)];
+      for (int i = hi; i > lo; i--)
+        v.mu[mu_off(i, k)] = v.mu[mu_off(i - 1, k)];
+      v.mu[mu_off(lo, k)] = t;
+    }
+    else
+    {
+      double t = v.mu[mu_off(lo, k)];
+      for (int i = lo; i < hi; i++)
+        v.mu[mu_off(i, k)] = v.mu[mu_off(i + 1, k)];
+      v.mu[mu_off(hi, k)] = t;
+    }
+  }
+  // r (columns k < lo)
+  for (int k = lane; k < lo; k += 32)
+  {
+    if (right)
+    {
+      double t = v.r[tri_off(hi) + k];
+      for (int i = hi; i > lo; i--)
+        v.r[tri_off(i) + k] = v.r[tri_off(i - 1) + k];
+      v.r[tri_off(lo) + k] = t;
+    }
+    else
+    {
+      double t = v.r[tri_off(lo) + k];
+      for (int i = lo; i < hi; i++)
+        v.r[tri_off(i) + k] = v.r[tri_off(i + 1) + k];
+      v.r[tri_off(hi) + k] = t;
+    }
+  }
+  // b and bf rows (all n columns)
+  for (int c = lane; c < v.n; c += 32)
+  {
+    if (right)
+    {
+      int64_t t = v.b[(size_t)hi * v.ldb + c];
+      double tf = v.bf[bf_off(hi, c, v.n)];
+      for (int i = hi; i > lo; i--)
+      {
+        v.b[(size_t)i * v.ldb + c] = v.b[(size_t)(i - 1) * v.ldb + c];
+        v.bf[bf_off(i, c, v.n)]    = v.bf[bf_off(i - 1, c, v.n)];
+      }
+      v.b[(size_t)lo * v.ldb + c] = t;
+      v.bf[bf_off(lo, c, v.n)]    = tf;
+    }
+    else
+    {
+      int64_t t = v.b[(size_t)lo * v.ldb + c];
+      double tf = v.bf[bf_off(lo, c, v.n)];
+      for (int i = lo; i < hi; i++)
+      {
+        v.b[(size_t)i * v.ldb + c] = v.b[(size_t)(i + 1) * v.ldb + c];
+        v.bf[bf_off(i, c, v.n)]    = v.bf[bf_off(i + 1, c, v.n)];
+      }
+      v.b[(size_t)hi * v.ldb + c] = t;
+      v.bf[bf_off(hi, c, v.n)]    = tf;
+    }
+  }
+  // gf: new(i,j) = old_sym(s(i), s(j)) on the known rows; rotate_gram_left only when old_r < nkr-1 and up to
+  // min(new_r, nkr-1) (gso.cpp:338-341)
+  {
+    const int ghi = right ? hi : min(hi, nkr - 1);
+    if (right || lo < nkr - 1)
+    {
+      const size_t beg = tri_off(lo), end = tri_off(nkr);
+      for (size_t t = beg + lane; t < end; t += 32)
+        v.scratch[t - beg] = v.gf[t];
+      __syncwarp();
+      for (int i = lo; i < nkr; i++)
+      {
+        int si = i;
+        if (i >= lo && i <= ghi)
+          si = right ? (i == lo ? ghi : i - 1) : (i == ghi ? lo : i + 1);
+        // columns touched: all j<=i if row i is rotated, else only j in [lo, ghi]
+        const int jb = (i <= ghi) ? 0 : lo, je = (i <= ghi) ? i : ghi;
+        for (int j = jb + lane; j <= je; j += 32)
+        {
+          int sj = j;
+          if (j >= lo && j <= ghi)
+            sj = right ? (j == lo ? ghi : j - 1) : (j == ghi ? lo : j + 1);
+          const int a = max(si, sj), b = min(si, sj);
+          v.gf[tri_off(i) + j] = v.scratch[tri_off(a) + b - beg];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // row_expo, gso_valid_cols (and init_row_size when the row leaves the known set): lane 0, tiny
+  if (lane == 0)
+  {
+    if (right)
+    {
+      int tv = v.valid[hi], te = v.row_expo[hi];
+      for (int i = hi; i > lo; i--)
+      {
+        v.valid[i]    = v.valid[i - 1];
+        v.row_expo[i] = v.row_expo[i - 1];
+      }
+      v.valid[lo] = tv;
+      if (v.row_expo_en)
+        v.row_expo[lo] = te;
+      else
+        v.row_expo[lo] = te;
+    }
+    else
+    {
+      int tv = v.valid[lo], te = v.row_expo[lo];
+      for (int i = lo; i < hi; i++)
+      {
+        v.valid[i]    = v.valid[i + 1];
+        v.row_expo[i] = v.row_expo[i + 1];
+      }
+      v.valid[hi]    = tv;
+      v.row_expo[hi] = te;
+      if (new_r >= nkr)
+      {
+        int ti = v.irs[lo];
+        for (int i = lo; i < hi; i++)
+          v.irs[i] = v.irs[i + 1];
+        v.irs[hi] = ti;
+      }
+    }
+  }
+  __syncwarp();
+  if (!right && new_r >= nkr && old_r < nkr)
+  {
+    const int nz = size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
+    if (lane == 0)
+    {
+      v.meta[M_NKR] = nkr - 1;
+      v.meta[M_NSR] = nkr - 1;
+      v.irs[new_r]  = max(nz, 1);
+    }
+  }
+  __syncwarp();
+}
+
+// set_r(i,j,f), gso_interface.h:739-746
+__device__ inline void warp_set_r(const View &v, int i, int j, double f, int lane)
+{
+  if (lane == 0)
+  {
+    v.r[tri_off(i) + j] = f;
+    if (v.valid[i] == j)
+      v.valid[i] = j + 1;
+  }
+  __syncwarp();
+}
+
+}  // namespace b200

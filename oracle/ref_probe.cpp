@@ -1,0 +1,419 @@
+/* ref_probe — TEST INFRASTRUCTURE (oracle side), not product code.
+ *
+ * A command interpreter over the UNMODIFIED reference library (oracle/_ref/libfplll.so, built from
+ * /root/reference by oracle/Makefile.ref).  It lets the parity tests drive the reference's own
+ * MatGSO<Z_NR<long|mpz_t>, FP_NR<double>> / MatHouseholder / LLL / BKZ / Enumeration objects one call at
+ * a time and dump their complete floating-point state as raw binary, and it is the `cpu_baseline`
+ * ("kind": "reference") timer of bench.py.  Nothing under fplll_b200/ links or executes it.
+ *
+ * Commands are read from stdin, one per line (see `help`).  Dump record layout (little endian):
+ *   int32 magic=0x4753304f, d, n, n_known_rows, n_known_cols, n_source_rows, flags, ztype(0=long,1=mpz)
+ *   int64 row_expo[d]; int32 gso_valid_cols[d]; int32 init_row_size[d]
+ *   f64 bf[d*n]; f64 gf[d*d]; f64 mu[d*d]; f64 r[d*d]; int64 b[d*n] (ztype long only, else absent)
+ */
+#include <fplll.h>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <thread>
+
+using namespace fplll;
+using namespace std;
+
+typedef MatGSO<Z_NR<long>, FP_NR<double>> GsoL;
+typedef MatGSO<Z_NR<mpz_t>, FP_NR<double>> GsoM;
+
+static ZZ_mat<mpz_t> Bm, Um, UTm;
+static ZZ_mat<long> Bl, Ul, UTl;
+static unique_ptr<GsoL> gl;
+static unique_ptr<GsoM> gm;
+static int gflags = 0;
+
+static double now()
+{
+  return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T> static void wr(FILE *f, const T *p, size_t n) { fwrite(p, sizeof(T), n, f); }
+
+template <class G> static void dump_state(G &m, const char *path, int ztype)
+{
+  FILE *f = fopen(path, "ab");
+  if (!f)
+  {
+    perror(path);
+    exit(2);
+  }
+  int d = m.d, n = m.b.get_cols();
+  int32_t hdr[8] = {0x4753304f, d, n, m.n_known_rows, m.n_known_cols, m.n_source_rows, gflags, ztype};
+  wr(f, hdr, 8);
+  vector<int64_t> re(d, 0);
+  if (m.enable_row_expo)
+    for (int i = 0; i < d; i++)
+      re[i] = m.row_expo[i];
+  wr(f, re.data(), d);
+  vector<int32_t> vc(d), irs(d);
+  for (int i = 0; i < d; i++)
+  {
+    vc[i]  = m.gso_valid_cols[i];
+    irs[i] = m.init_row_size[i];
+  }
+  wr(f, vc.data(), d);
+  wr(f, irs.data(), d);
+  vector<double> buf((size_t)d * n);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      buf[(size_t)i * n + j] = m.bf(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  buf.assign((size_t)d * d, 0.0);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++)
+      buf[(size_t)i * d + j] = m.gf(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++)
+      buf[(size_t)i * d + j] = m.mu(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++)
+      buf[(size_t)i * d + j] = m.r(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  fclose(f);
+}
+
+static void dump_b_long(const char *path)
+{
+  FILE *f = fopen(path, "ab");
+  int d = Bl.get_rows(), n = Bl.get_cols();
+  vector<int64_t> buf((size_t)d * n);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      buf[(size_t)i * n + j] = Bl(i, j).get_si();
+  wr(f, buf.data(), buf.size());
+  fclose(f);
+}
+
+template <class G> static void time_update_row(G &m, int i, int reps, int invalidate)
+{
+  /* times what LLL's babai() pays per iteration on row i: row_op_end(i,i+1) [update_bf + invalidation]
+     followed by update_gso_row(i, i)  (gso_interface.cpp:32-53,131-164).  invalidate=0 keeps gf valid (g=0) */
+  m.update_gso();
+  double t0 = now();
+  for (int rep = 0; rep < reps; rep++)
+  {
+    if (invalidate)
+    {
+      m.row_op_begin(i, i + 1);
+      m.row_op_end(i, i + 1);
+    }
+    else
+      m.invalidate_gso_row(i, 0);
+    m.update_gso_row(i, i);
+  }
+  double t1 = now();
+  printf("time_update_row i=%d reps=%d invalidate=%d sec=%.9f per_call_us=%.4f\n", i, reps, invalidate,
+         t1 - t0, (t1 - t0) / reps * 1e6);
+}
+
+/* Multi-threaded CPU baseline: T threads, each owning `per` private copies of the current long basis, run
+ * `reps` x { row_op_end(i,i+1); update_gso_row(i,i) } on every copy (distinct objects may run concurrently,
+ * README.md:310).  Prints the aggregate wall time. */
+static void time_update_row_mt(int i, int reps, int threads, int per)
+{
+  vector<thread> th;
+  vector<double> secs(threads);
+  double t0 = now();
+  for (int t = 0; t < threads; t++)
+    th.emplace_back([&, t]() {
+      vector<ZZ_mat<long>> bs(per, Bl);
+      ZZ_mat<long> eu, eut;
+      vector<unique_ptr<GsoL>> gs;
+      for (int p = 0; p < per; p++)
+      {
+        gs.emplace_back(new GsoL(bs[p], eu, eut, gflags));
+        gs.back()->update_gso();
+      }
+      double a = now();
+      for (int rep = 0; rep < reps; rep++)
+        for (int p = 0; p < per; p++)
+        {
+          gs[p]->row_op_begin(i, i + 1);
+          gs[p]->row_op_end(i, i + 1);
+          gs[p]->update_gso_row(i, i);
+        }
+      secs[t] = now() - a;
+    });
+  for (auto &x : th)
+    x.join();
+  double t1 = now(), mx = 0;
+  for (double s : secs)
+    mx = max(mx, s);
+  printf("time_update_row_mt i=%d reps=%d threads=%d per=%d calls=%ld timed_sec=%.9f wall_sec=%.6f\n", i, reps,
+         threads, per, (long)reps * threads * per, mx, t1 - t0);
+}
+
+static void time_update_gso_mt(int reps, int threads, int per)
+{
+  vector<thread> th;
+  vector<double> secs(threads);
+  for (int t = 0; t < threads; t++)
+    th.emplace_back([&, t]() {
+      vector<ZZ_mat<long>> bs(per, Bl);
+      ZZ_mat<long> eu, eut;
+      vector<unique_ptr<GsoL>> gs;
+      for (int p = 0; p < per; p++)
+        gs.emplace_back(new GsoL(bs[p], eu, eut, gflags));
+      double a = now();
+      for (int rep = 0; rep < reps; rep++)
+        for (int p = 0; p < per; p++)
+        {
+          gs[p]->row_op_begin(0, gs[p]->d);
+          gs[p]->row_op_end(0, gs[p]->d);
+          gs[p]->update_gso();
+        }
+      secs[t] = now() - a;
+    });
+  for (auto &x : th)
+    x.join();
+  double mx = 0;
+  for (double s : secs)
+    mx = max(mx, s);
+  printf("time_update_gso_mt reps=%d threads=%d per=%d calls=%ld timed_sec=%.9f\n", reps, threads, per,
+         (long)reps * threads * per, mx);
+}
+
+int main(int argc, char **argv)
+{
+  string line;
+  while (getline(cin, line))
+  {
+    istringstream is(line);
+    string c;
+    if (!(is >> c) || c[0] == '#')
+      continue;
+    if (c == "help")
+    {
+      puts("load P | save P | tolong | gso l|m FLAGS | update_gso | update_row I J | discover_all | "
+           "row_addmul_we I J X E | row_op_begin F L | row_op_end F L | move_row O N | row_swap I J | "
+           "set_r I J V | dump P | dumpb P | lll DELTA ETA METHOD FLOAT FLAGS | islll DELTA ETA | "
+           "time_update_row I REPS INV | time_update_row_mt I REPS T PER | time_update_gso_mt REPS T PER");
+    }
+    else if (c == "load")
+    {
+      string p;
+      is >> p;
+      ifstream f(p);
+      if (!f)
+      {
+        fprintf(stderr, "cannot open %s\n", p.c_str());
+        return 2;
+      }
+      f >> Bm;
+      gl.reset();
+      gm.reset();
+      printf("load %d %d\n", Bm.get_rows(), Bm.get_cols());
+    }
+    else if (c == "save")
+    {
+      string p;
+      is >> p;
+      ofstream f(p);
+      if (gl)
+        f << Bl << endl;
+      else
+        f << Bm << endl;
+    }
+    else if (c == "tolong")
+    {
+      int d = Bm.get_rows(), n = Bm.get_cols();
+      Bl.resize(d, n);
+      for (int i = 0; i < d; i++)
+        for (int j = 0; j < n; j++)
+          Bl(i, j) = Bm(i, j).get_si();
+      printf("tolong ok\n");
+    }
+    else if (c == "gso")
+    {
+      string t;
+      is >> t >> gflags;
+      if (t == "l")
+      {
+        gm.reset();
+        gl.reset(new GsoL(Bl, Ul, UTl, gflags));
+      }
+      else
+      {
+        gl.reset();
+        gm.reset(new GsoM(Bm, Um, UTm, gflags));
+      }
+    }
+    else if (c == "update_gso")
+    {
+      bool ok = gl ? gl->update_gso() : gm->update_gso();
+      printf("update_gso %d\n", (int)ok);
+    }
+    else if (c == "discover_all")
+    {
+      if (gl)
+        gl->discover_all_rows();
+      else
+        gm->discover_all_rows();
+    }
+    else if (c == "update_row")
+    {
+      int i, j;
+      is >> i >> j;
+      bool ok = gl ? gl->update_gso_row(i, j) : gm->update_gso_row(i, j);
+      printf("update_row %d %d %d\n", i, j, (int)ok);
+    }
+    else if (c == "row_addmul_we")
+    {
+      int i, j;
+      double x;
+      long e;
+      is >> i >> j >> x >> e;
+      FP_NR<double> fx = x;
+      if (gl)
+        gl->row_addmul_we(i, j, fx, e);
+      else
+        gm->row_addmul_we(i, j, fx, e);
+    }
+    else if (c == "row_op_begin")
+    {
+      int a, b;
+      is >> a >> b;
+      if (gl)
+        gl->row_op_begin(a, b);
+      else
+        gm->row_op_begin(a, b);
+    }
+    else if (c == "row_op_end")
+    {
+      int a, b;
+      is >> a >> b;
+      if (gl)
+        gl->row_op_end(a, b);
+      else
+        gm->row_op_end(a, b);
+    }
+    else if (c == "move_row")
+    {
+      int a, b;
+      is >> a >> b;
+      if (gl)
+        gl->move_row(a, b);
+      else
+        gm->move_row(a, b);
+    }
+    else if (c == "row_swap")
+    {
+      int a, b;
+      is >> a >> b;
+      if (gl)
+        gl->row_swap(a, b);
+      else
+        gm->row_swap(a, b);
+    }
+    else if (c == "set_r")
+    {
+      int i, j;
+      double v;
+      is >> i >> j >> v;
+      FP_NR<double> f = v;
+      if (gl)
+        gl->set_r(i, j, f);
+      else
+        gm->set_r(i, j, f);
+    }
+    else if (c == "dump")
+    {
+      string p;
+      is >> p;
+      if (gl)
+      {
+        dump_state(*gl, p.c_str(), 0);
+        dump_b_long(p.c_str());
+      }
+      else
+        dump_state(*gm, p.c_str(), 1);
+    }
+    else if (c == "lll")
+    {
+      /* lll DELTA ETA METHOD(wrapper|proved|heuristic|fast) FLOAT(default|double|...) FLAGS ; on the mpz matrix */
+      double delta, eta;
+      string ms, fs;
+      int fl;
+      is >> delta >> eta >> ms >> fs >> fl;
+      LLLMethod me = ms == "wrapper" ? LM_WRAPPER : ms == "proved" ? LM_PROVED : ms == "fast" ? LM_FAST : LM_HEURISTIC;
+      FloatType ft = fs == "double" ? FT_DOUBLE : fs == "mpfr" ? FT_MPFR : fs == "ld" ? FT_LONG_DOUBLE : FT_DEFAULT;
+      double t0 = now();
+      int st    = lll_reduction(Bm, delta, eta, me, ft, 0, fl);
+      printf("lll status=%d sec=%.6f\n", st, now() - t0);
+    }
+    else if (c == "lll_long")
+    {
+      /* LLL on the long matrix through the same code path bkz.cpp:826-836 uses: MatGSO<long,double>, GSO_ROW_EXPO */
+      double delta, eta;
+      is >> delta >> eta;
+      ZZ_mat<long> eu, eut;
+      GsoL m(Bl, eu, eut, GSO_ROW_EXPO);
+      LLLReduction<Z_NR<long>, FP_NR<double>> lll(m, delta, eta, LLL_DEFAULT);
+      double t0 = now();
+      lll.lll();
+      printf("lll_long status=%d sec=%.6f swaps=%d\n", lll.status, now() - t0, lll.n_swaps);
+    }
+    else if (c == "islll")
+    {
+      double delta, eta;
+      is >> delta >> eta;
+      ZZ_mat<mpz_t> B2;
+      if (Bl.get_rows() > 0 && gl)
+      {
+        B2.resize(Bl.get_rows(), Bl.get_cols());
+        for (int i = 0; i < Bl.get_rows(); i++)
+          for (int j = 0; j < Bl.get_cols(); j++)
+            B2(i, j) = Bl(i, j).get_si();
+      }
+      else
+        B2 = Bm;
+      int old = FP_NR<mpfr_t>::set_prec(512);
+      ZZ_mat<mpz_t> eu, eut;
+      MatGSO<Z_NR<mpz_t>, FP_NR<mpfr_t>> M(B2, eu, eut, GSO_INT_GRAM);
+      int ok = is_lll_reduced<Z_NR<mpz_t>, FP_NR<mpfr_t>>(M, delta, eta);
+      FP_NR<mpfr_t>::set_prec(old);
+      printf("islll %d\n", ok);
+    }
+    else if (c == "time_update_row")
+    {
+      int i, reps, inv;
+      is >> i >> reps >> inv;
+      if (gl)
+        time_update_row(*gl, i, reps, inv);
+      else
+        time_update_row(*gm, i, reps, inv);
+    }
+    else if (c == "time_update_row_mt")
+    {
+      int i, reps, t, per;
+      is >> i >> reps >> t >> per;
+      time_update_row_mt(i, reps, t, per);
+    }
+    else if (c == "time_update_gso_mt")
+    {
+      int reps, t, per;
+      is >> reps >> t >> per;
+      time_update_gso_mt(reps, t, per);
+    }
+    else
+    {
+      fprintf(stderr, "unknown command: %s\n", c.c_str());
+      return 2;
+    }
+    fflush(stdout);
+  }
+  return 0;
+}

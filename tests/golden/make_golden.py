@@ -1,0 +1,96 @@
+"""Regenerates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built from /root/reference by
+oracle/Makefile.ref).  Run in the build container only:  python tests/golden/make_golden.py
+Inputs come from the reference's own latticegen (default seed), never from a re-implementation."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import oracle as O  # noqa: E402
+import helpers as H  # noqa: E402
+
+TMP = "/tmp/lat"
+os.makedirs(TMP, exist_ok=True)
+
+
+def save_state(path, rec, extra=None):
+    keys = ["d", "n", "n_known_rows", "n_known_cols", "n_source_rows", "flags", "row_expo", "gso_valid_cols",
+            "init_row_size", "bf", "gf", "mu", "r", "b"]
+    out = {k: rec[k] for k in keys if k in rec}
+    out.update(extra or {})
+    np.savez_compressed(path, **out)
+
+
+def gen(args, name):
+    p = os.path.join(TMP, name)
+    if not os.path.exists(p):
+        open(p, "w").write(O.latticegen(args))
+    return p
+
+
+def main():
+    # --- config #1 input: latticegen u 40 40 (md5 a6fe01e1...) -------------------------------
+    u40 = np.array(O.read_matrix(gen(["u", 40, 40], "u40.txt")), dtype=np.int64)
+    s = O.RefSession(u40)
+    s.cmd("update_gso")
+    s.dump_state()
+    _, recs = s.run()
+    save_state(os.path.join(HERE, "u40_update_gso.npz"), recs[0])
+
+    # op-sequence trace on u40 (state machine: row ops, move_row, partial updates), dumped after every op group
+    rng = np.random.default_rng(20260923)
+    ops = H.random_op_script(rng, 40, 60)
+    s = O.RefSession(u40)
+    marks = []
+    for k, op in enumerate(ops):
+        for line in H.ops_to_ref_script([op]):
+            s.lines.append(line)
+        if op[0] in ("move_row", "update_gso") or (op[0] in ("row_op_end", "update_rows_to") and k % 3 == 0):
+            s.dump_state()
+            marks.append(k)
+    _, recs = s.run()
+    assert len(recs) == len(marks)
+    import json
+    pack = {"ops_json": np.frombuffer(json.dumps(ops).encode(), dtype=np.uint8), "marks": np.array(marks),
+            "b0": u40}
+    for t, r in enumerate(recs):
+        for key in ["n_known_rows", "n_known_cols", "n_source_rows"]:
+            pack["s%d_%s" % (t, key)] = np.int32(r[key])
+        for key in ["row_expo", "gso_valid_cols", "init_row_size", "bf", "gf", "mu", "r", "b"]:
+            pack["s%d_%s" % (t, key)] = r[key]
+    np.savez_compressed(os.path.join(HERE, "u40_ops_trace.npz"), **pack)
+
+    # reference LLL on u40 through the <long,double> code path (MatGSO<long,double>+LLLReduction, GSO_ROW_EXPO)
+    mat = os.path.join(TMP, "u40.txt")
+    out = O.run_ref("load %s\ntolong\nlll_long 0.99 0.51\ngso l 2\nsave %s/u40_lll_long.txt\n" % (mat, TMP))
+    st = dict(tok.split("=") for tok in out.split("lll_long")[1].split() if "=" in tok)
+    red = np.array(O.read_matrix(TMP + "/u40_lll_long.txt"), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "u40_lll_long.npz"), b_in=u40, b_out=red, status=np.int32(st["status"]),
+                        n_swaps=np.int32(st["swaps"]))
+
+    # --- config #2/#5 input after the host wrapper LLL (bkz.cpp:873-875): int64 regime dim-200 -------------
+    r200 = gen(["r", 200, 2000], "r200.txt")
+    red_path = os.path.join(TMP, "r200_lll.txt")
+    if not os.path.exists(red_path):
+        O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (r200, red_path), timeout=900)
+    b200 = np.array(O.read_matrix(red_path), dtype=np.int64)
+    s = O.RefSession(b200)
+    s.cmd("update_gso")
+    s.dump_state()
+    _, recs = s.run()
+    rec = recs[0]
+    # keep the fixture small: b + the derived state in compact form (mu/r lower triangles as float64)
+    tl = np.tril_indices(200)
+    np.savez_compressed(os.path.join(HERE, "r200_lll_update_gso.npz"), b=b200, row_expo=rec["row_expo"],
+                        gso_valid_cols=rec["gso_valid_cols"], init_row_size=rec["init_row_size"],
+                        n_known_rows=np.int32(rec["n_known_rows"]), n_known_cols=np.int32(rec["n_known_cols"]),
+                        n_source_rows=np.int32(rec["n_source_rows"]),
+                        mu_tril=rec["mu"][tl], r_tril=rec["r"][tl], gf_tril=rec["gf"][tl])
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+"""GPU parity tests: the CUDA GSO path (through the C-ABI of include/b200gso.h) against the CPU oracle and the
+committed reference dumps.  Everything is integer / order-preserving fp64, so the bar is BIT-EXACT."""
+import json
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fplll_b200
+    return fplll_b200
+
+
+def _gold_state(z, prefix=""):
+    g = lambda k: z[prefix + k]
+    return dict(n_known_rows=int(g("n_known_rows")), n_known_cols=int(g("n_known_cols")),
+                n_source_rows=int(g("n_source_rows")), row_expo=g("row_expo"), gso_valid_cols=g("gso_valid_cols"),
+                init_row_size=g("init_row_size"), bf=g("bf"), gf=g("gf"), mu=g("mu"), r=g("r"), b=g("b"))
+
+
+def test_update_gso_u40_vs_reference_dump(fb):
+    z = H.gold("u40_update_gso.npz")
+    m = fb.MatGSO(z["b"])
+    assert m.update_gso().all()
+    H.assert_state_equal(H.lattice_state(m.state(), 0), _gold_state(z), "u40")
+
+
+def test_ops_trace_u40_vs_reference_dump(fb):
+    z = H.gold("u40_ops_trace.npz")
+    ops = json.loads(bytes(z["ops_json"]).decode())
+    marks = list(z["marks"])
+    m = fb.MatGSO(z["b0"])
+    t = 0
+    for k, op in enumerate(ops):
+        H.apply_ops(m, [tuple(op)])
+        if t < len(marks) and marks[t] == k:
+            H.assert_state_equal(H.lattice_state(m.state(), 0), _gold_state(z, "s%d_" % t), "op %d %s" % (k, op))
+            t += 1
+    assert t == len(marks)
+
+
+def test_update_gso_r200_vs_reference_dump(fb):
+    """BASELINE config #2/#5 state: the wrapper-LLL-reduced latticegen r 200 2000 basis (int64 regime)."""
+    z = H.gold("r200_lll_update_gso.npz")
+    m = fb.MatGSO(z["b"])
+    assert m.update_gso().all()
+    s = H.lattice_state(m.state(), 0)
+    tl = np.tril_indices(200)
+    off = tl[0] != tl[1]
+    assert H.eq_f64(s["mu"][tl][off], z["mu_tril"][off])
+    assert H.eq_f64(s["r"][tl], z["r_tril"])
+    assert H.eq_f64(s["gf"][tl], z["gf_tril"])
+    assert np.array_equal(s["row_expo"], z["row_expo"])
+
+
+@pytest.mark.parametrize("seed,d,n,bits,flags", [(1, 12, 12, 20, 2), (2, 33, 40, 30, 2), (3, 64, 65, 12, 0),
+                                                  (4, 7, 9, 50, 2), (5, 97, 97, 25, 2), (6, 130, 131, 10, 2)])
+def test_random_ops_vs_oracle(fb, seed, d, n, bits, flags):
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-(1 << bits), 1 << bits, size=(d, n), dtype=np.int64)
+    ops = H.random_op_script(rng, d, 50)
+    mo = O.OracleGSO(b, flags)
+    md = fb.MatGSO(b, flags)
+    for k, op in enumerate(ops):
+        H.apply_ops(mo, [op])
+        H.apply_ops(md, [op])
+        if k % 7 == 0 or k == len(ops) - 1:
+            H.assert_state_equal(H.lattice_state(md.state(), 0), mo.state(), "seed %d op %d %s" % (seed, k, op))
+
+
+def test_batch_lattices_are_independent(fb):
+    """a batch of different lattices == each lattice run alone (the replica axis of SURVEY §8e)."""
+    rng = np.random.default_rng(11)
+    B, d, n = 9, 24, 30
+    b = rng.integers(-1000, 1000, size=(B, d, n), dtype=np.int64)
+    md = fb.MatGSO(b)
+    assert md.update_gso().all()
+    x = rng.integers(-5, 6, size=B).astype(np.float64)
+    md.row_addmul_we(7, 3, x, 0)
+    md.row_op_end(7, 8)
+    md.move_row(20, 5)
+    md.update_gso()
+    st = md.state()
+    for l in range(B):
+        mo = O.OracleGSO(b[l])
+        mo.update_gso()
+        mo.row_addmul_we(7, 3, x[l], 0)
+        mo.row_op_end(7, 8)
+        mo.move_row(20, 5)
+        mo.update_gso()
+        H.assert_state_equal(H.lattice_state(st, l), mo.state(), "lattice %d" % l)
+
+
+def test_ragged_knapsack_and_zero_row(fb):
+    rng = np.random.default_rng(9)
+    d = 10
+    b = np.zeros((d, d + 1), np.int64)
+    b[:, 0] = rng.integers(1, 1 << 40, size=d)
+    b[np.arange(d), np.arange(d) + 1] = 1
+    b[4] = 0
+    mo, md = O.OracleGSO(b), fb.MatGSO(b)
+    for t in range(3):
+        assert mo.update_gso_row(t, t) and md.update_gso_row(t, t).all()
+    H.assert_state_equal(H.lattice_state(md.state(), 0), mo.state(), "partial discovery")
+    mo.move_row(1, 9)
+    md.move_row(1, 9)
+    H.assert_state_equal(H.lattice_state(md.state(), 0), mo.state(), "row leaves the known set")
+
+
+def test_gso_failure_reported_like_reference(fb):
+    """duplicate row -> r(j,j) == 0 -> mu = x/0 not finite -> update_gso_row returns false (gso_interface.cpp:156)."""
+    b = np.array([[3, 1, 4], [3, 1, 4], [1, 5, 9]], dtype=np.int64)
+    mo, md = O.OracleGSO(b), fb.MatGSO(b)
+    assert mo.update_gso_row(0) and md.update_gso_row(0).all()
+    assert mo.update_gso_row(1) and md.update_gso_row(1).all()
+    assert mo.update_gso_row(2) is False
+    assert not md.update_gso_row(2).any()
+
+
+def test_device_lll_u40_equals_reference_basis(fb):
+    """BASELINE config #1: LLL delta=0.99 on latticegen u 40 40 — the device LLL must walk the reference's exact
+    basis trajectory (same swaps, same output basis as MatGSO<long,double>+LLLReduction of the reference)."""
+    z = H.gold("u40_lll_long.npz")
+    m = fb.MatGSO(z["b_in"])
+    st, stats = m.lll(0.99, 0.51)
+    assert st[0] == int(z["status"]) == 0
+    assert stats["n_swaps"][0] == int(z["n_swaps"])
+    assert np.array_equal(m.b[0], z["b_out"])
+
+
+@pytest.mark.parametrize("seed,d,bits", [(21, 16, 20), (22, 48, 30), (23, 70, 16)])
+def test_device_lll_random_vs_oracle(fb, seed, d, bits):
+    rng = np.random.default_rng(seed)
+    B = 5
+    b = rng.integers(-(1 << bits), 1 << bits, size=(B, d, d), dtype=np.int64)
+    b[1, 3] = 0  # a zero vector: parked at the end (lll.cpp:66-69)
+    b[2, 5] = b[2, 4]  # a dependency: discovered as a zero vector during reduction (lll.cpp:144-150)
+    md = fb.MatGSO(b)
+    st, stats = md.lll(0.99, 0.51)
+    out = md.b
+    for l in range(B):
+        mo = O.OracleGSO(b[l])
+        res = mo.lll(0.99, 0.51)
+        assert st[l] == res["status"], "lattice %d status" % l
+        assert stats["n_swaps"][l] == res["n_swaps"]
+        assert stats["zeros"][l] == res["zeros"]
+        assert np.array_equal(out[l], mo.state()["b"]), "lattice %d basis" % l
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not shipped")
+def test_device_lll_output_passes_reference_is_lll_reduced(fb, tmp_path):
+    """the reference's own acceptance check: is_lll_reduced<Z_NR<mpz_t>, FP_NR<mpfr_t>> (lll.cpp:226-258)."""
+    z = H.gold("u40_lll_long.npz")
+    b = z["b_in"].copy()
+    assert fb.lll_reduction(b, 0.99, 0.51) == 0
+    p = tmp_path / "out.txt"
+    O.write_matrix(str(p), b)
+    out = O.run_ref("load %s\nislll 0.99 0.51\n" % p)
+    assert "islll 1" in out
