@@ -1,0 +1,243 @@
+#!/usr/bin/env python
+"""bench.py — GSO-update throughput on B200 (the BASELINE.json metric), one JSON line on stdout.
+
+Step  = what LLLReduction::babai pays per iteration on the GSO state of every lattice of a batch
+        (lll.cpp:166-224):  row_op_end(kappa, kappa+1)  [update_bf + Gram/GSO invalidation, gso_interface.cpp:32-53]
+        followed by  update_gso_row(kappa, kappa)  [Gram row recompute + forward substitution,
+        gso_interface.cpp:131-164], at kappa = d-1 of dim-200 (200 x 201) lattices — the shape of BASELINE
+        configs #2/#5.  Independent lattices are the only axis the GSO path shards on (replicas),
+        so N GPUs = N independent batches, no data-path collective, scaling "weak".
+value = algorithmic bytes of update_gso_row (8*[(i+1)*n + i(i-1)/2 + 4(i+1)] per lattice, Gram row
+        invalid) * lattices * steps / device time of the timed region (CUDA events on the launching stream,
+        max over ranks) — inputs resident in HBM.
+e2e   = same metric through the C-ABI with HOST buffers: every step uploads each lattice's refreshed integer row
+        kappa from pinned host memory (b200gso_upload_row = write b[kappa] + row_op_end), runs update_gso_row and
+        reads rows kappa of mu and r back (b200gso_get_mu_r_row) — the protocol of a host-resident LLL driver.
+--impl reference : the UNMODIFIED reference (oracle/_ref/ref_probe over libfplll.so) doing the same step on the
+        box's host cores, all threads; bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, N_COLS = 200, 201
+KAPPA = D - 1
+METRIC = "gso_update_row_GBps"
+
+
+def alg_bytes_update_row(i, n, g=1):
+    return 8 * ((i + 1) * n * g + i * (i - 1) // 2 + 4 * (i + 1))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(seconds_target=12.0):
+    """Times the reference's own CPU path (oracle/_ref) on all host threads: the same step on dim-200 lattices."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    if not O.have_ref():
+        return None
+    rng = np.random.default_rng(12345)
+    b = rng.integers(-(1 << 20), 1 << 20, size=(D, N_COLS), dtype=np.int64)
+    tmp = tempfile.mkdtemp(prefix="bench_ref_")
+    mat = os.path.join(tmp, "b.txt")
+    O.write_matrix(mat, b)
+    per = 4  # lattices per thread
+    # calibrate with a short run, then size reps for ~seconds_target
+    def run(reps):
+        out = O.run_ref("load %s\ntolong\ngso l 2\ntime_update_row_mt %d %d %d %d\n" % (mat, KAPPA, reps, cores, per))
+        tok = dict(t.split("=") for t in out.split("time_update_row_mt")[1].split() if "=" in t)
+        return float(tok["timed_sec"]), int(tok["calls"])
+    reps = 50
+    t, calls = run(reps)
+    while t < 0.5 * seconds_target and reps < (1 << 24):
+        reps = int(reps * min(8.0, max(1.5, 1.1 * seconds_target / max(t, 1e-3))))
+        t, calls = run(reps)
+    gbps = calls * alg_bytes_update_row(KAPPA, N_COLS) / t / 1e9
+    return {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "reference",
+            "sample": "%d calls of {row_op_end(%d,%d); update_gso_row(%d)} on %d private dim-%d MatGSO<long,double> "
+                      "objects, %d threads, %.1f s" % (calls, KAPPA, KAPPA + 1, KAPPA, cores * per, D, cores, t),
+            "us_per_call_per_thread": t / (calls / cores) * 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="lattices per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = ("batched {row_op_end(%d,%d); update_gso_row(%d,%d)} on %d independent dim-%d (%dx%d) int64 lattices per GPU"
+                % (KAPPA, KAPPA + 1, KAPPA, KAPPA, a.batch, D, D, N_COLS))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        steps_v = []
+        for _ in range(max(1, min(a.steps, 3))):
+            steps_v.append(cpu_reference(seconds_target=8.0))
+        ref = max(steps_v, key=lambda r: r["value"])
+        line = {"metric": METRIC, "value": ref["value"], "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload.replace("%d independent" % a.batch, "threads*4 private"),
+                           "note": "reference fplll 5.5.0 CPU path (oracle/_ref), all host threads"},
+                "cpu_baseline": ref,
+                "e2e": {"value": ref["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import fplll_b200 as fb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = a.batch
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    dev_b = torch.randint(-(1 << 20), 1 << 20, (B, D, N_COLS), dtype=torch.int64, device="cuda", generator=gen)
+    import ctypes as C
+    from fplll_b200.gso import _lib, _ck
+    m = fb.MatGSO.__new__(fb.MatGSO)
+    m.batch, m.d, m.n, m.flags, m.enable_row_expo = B, D, N_COLS, fb.GSO_ROW_EXPO, True
+    m._h = C.c_void_p()
+    _ck(_lib().b200gso_create(C.byref(m._h), B, D, N_COLS, fb.GSO_ROW_EXPO, local), "create")
+    torch.cuda.synchronize()
+    _ck(_lib().b200gso_set_basis_dev(m._h, C.c_void_p(dev_b.data_ptr())), "set_basis_dev")
+    assert m.update_gso().all()  # all rows valid: the state LLL is in when it revisits kappa
+    m.sync()
+    del dev_b
+
+    per_lat = alg_bytes_update_row(KAPPA, N_COLS)
+    # ---- device-resident timing ---------------------------------------------------------------------------
+    m.time_update_row(KAPPA, a.warmup, True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_update, ms_total = m.time_update_row(KAPPA, a.steps, True)
+    torch.cuda.synchronize()
+    if dist:
+        t = torch.tensor([ms_total, ms_update], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_update = float(t[0]), float(t[1])
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * per_lat * a.steps / (ms_total * 1e-3) / 1e9
+    kern_gbps = B * per_lat / (ms_update * 1e-3) / 1e9
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
+    rows = torch.randint(-(1 << 20), 1 << 20, (B, N_COLS), dtype=torch.int64).pin_memory().numpy()
+    def e2e_step():
+        m.upload_row(KAPPA, rows)          # H2D B*n*8 + row_op_end
+        ok = m.update_gso_row(KAPPA)       # D2H B*4
+        mu, r, v = m.get_mu_r_row(KAPPA)   # D2H 2*B*d*8 + B*4
+        return ok
+    for _ in range(a.warmup):
+        e2e_step()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ok = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert ok.all()
+    if dist:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_val = world * B * per_lat * a.steps / e2e_s / 1e9
+    h2d = B * N_COLS * 8
+    d2h = 2 * B * D * 8 + 2 * B * 4
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "entries": "uniform int in [-2^20, 2^20)", "flags": "GSO_ROW_EXPO",
+                           "state_bytes_per_gpu": int(B * 1.39e6), "l2": "inputs larger than L2 (state >> 126 MB)",
+                           "algorithmic_bytes_per_lattice": per_lat},
+                "roofline": {"bound": "hbm", "kernel": "k_update_row (update_gso_row, g=1)", "achieved": kern_gbps,
+                             "peak": peak, "unit": "GB/s", "frac": kern_gbps / peak, "peak_source": peak_src,
+                             "traffic": None, "ms_per_launch": ms_update},
+                "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s / a.steps * 1e3},
+                "gpu_launches": 2 * a.steps, "clocks": clocks}
+        if not a.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference()
+            except Exception as ex:  # the reference build did not travel: say so, do not fake it
+                line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -690,14 +690,15 @@ int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats
   return 0;
 }
 
-int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_per_launch)
+int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_update_mean, float *ms_total)
 {
-  if (!h || !ms_per_launch || reps <= 0 || i < 0 || i >= h->S.d)
+  if (!h || reps <= 0 || i < 0 || i >= h->S.d)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+  std::vector<cudaEvent_t> ev(2 * (size_t)reps + 2);
   for (auto &e : ev)
     CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[2 * reps], h->stream));
   for (int r = 0; r < reps; r++)
   {
     if (invalidate)
@@ -708,6 +709,7 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
     k_update_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, i, h->d_ok);
     CK(cudaEventRecord(ev[2 * r + 1], h->stream));
   }
+  CK(cudaEventRecord(ev[2 * reps + 1], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   double tot = 0;
   for (int r = 0; r < reps; r++)
@@ -716,9 +718,14 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
     CK(cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]));
     tot += ms;
   }
+  float all = 0;
+  CK(cudaEventElapsedTime(&all, ev[2 * reps], ev[2 * reps + 1]));
   for (auto &e : ev)
     cudaEventDestroy(e);
-  *ms_per_launch = (float)(tot / reps);
+  if (ms_update_mean)
+    *ms_update_mean = (float)(tot / reps);
+  if (ms_total)
+    *ms_total = all;
   CK(cudaGetLastError());
   return 0;
 }

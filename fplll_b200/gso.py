@@ -41,7 +41,7 @@ def _lib():
         L.b200gso_get_state.argtypes = [vp, dp, dp, dp, dp, i64p, ip, ip, ip]
         L.b200gso_get_mu_r_row.argtypes = [vp, i, dp, dp, ip]
         L.b200gso_lll.argtypes = [vp, C.c_double, C.c_double, ip, lp]
-        L.b200gso_time_update_row.argtypes = [vp, i, i, i, _P(C.c_float)]
+        L.b200gso_time_update_row.argtypes = [vp, i, i, i, _P(C.c_float), _P(C.c_float)]
         L.b200gso_sync.argtypes = [vp]
         _sig_done = True
     return L
@@ -164,9 +164,11 @@ class MatGSO:
         return st, dict(n_swaps=stats[:, 0], final_kappa=stats[:, 1], zeros=stats[:, 2], babai_iters=stats[:, 3])
 
     def time_update_row(self, i, reps, invalidate=True):
-        ms = C.c_float()
-        _ck(_lib().b200gso_time_update_row(self._h, i, reps, 1 if invalidate else 0, C.byref(ms)), "time_update_row")
-        return ms.value
+        """returns (mean ms of one update_gso_row launch, total ms of the `reps` steps), CUDA events on the handle's stream"""
+        ms, tot = C.c_float(), C.c_float()
+        _ck(_lib().b200gso_time_update_row(self._h, i, reps, 1 if invalidate else 0, C.byref(ms), C.byref(tot)),
+            "time_update_row")
+        return ms.value, tot.value
 
     def sync(self):
         _ck(_lib().b200gso_sync(self._h), "sync")

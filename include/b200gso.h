@@ -100,10 +100,11 @@ int b200gso_get_mu_r_row(b200gso_t *h, int i, double *mu_row, double *r_row, int
  * stats (may be NULL): batch*4 = {n_swaps, final_kappa, zeros, babai_iterations}. */
 int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats);
 
-/* Timing helper for bench.py: runs `reps` back-to-back launches of { row_op_end(i,i+1); update_gso_row(i,i) }
- * (invalidate != 0) or { invalidate_gso_row(i,0); update_gso_row(i,i) } on the handle's stream and returns the
- * mean device time of ONE update_gso_row launch in milliseconds, measured with CUDA events on that stream. */
-int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_per_launch);
+/* Timing helper for bench.py: runs `reps` back-to-back steps { row_op_end(i,i+1); update_gso_row(i,i) }
+ * (invalidate != 0) or { invalidate_gso_row(i,0); update_gso_row(i,i) } on the handle's stream, timed with CUDA
+ * events ON THAT STREAM: *ms_update_mean = mean device time of ONE update_gso_row launch (events around each
+ * launch), *ms_total = device time of the whole region (all 2*reps launches).  Either pointer may be NULL. */
+int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_update_mean, float *ms_total);
 
 /* Synchronise the handle's stream (all calls above are stream-ordered on one stream per handle). */
 int b200gso_sync(b200gso_t *h);

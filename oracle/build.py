@@ -22,8 +22,13 @@ def build_oracle(force=False):
 def build_ref(jobs=8):
     if not os.path.isdir("/root/reference/fplll"):
         return None  # GPU box: use the prebuilt oracle/_ref that travelled with the snapshot
-    subprocess.check_call(["make", "-f", os.path.join(HERE, "Makefile.ref"), "-j%d" % jobs, "all"],
-                          cwd=HERE, stdout=subprocess.DEVNULL)
+    need = ["libfplll.so", "fplll", "latticegen", "ref_probe", "strategies/default.json"]
+    probe_src = os.path.join(HERE, "ref_probe.cpp")
+    fresh = all(os.path.exists(os.path.join(HERE, "_ref", f)) for f in need) and \
+        os.path.getmtime(os.path.join(HERE, "_ref", "ref_probe")) >= os.path.getmtime(probe_src)
+    if not fresh:
+        subprocess.check_call(["make", "-f", os.path.join(HERE, "Makefile.ref"), "-j%d" % jobs, "all"],
+                              cwd=HERE, stdout=subprocess.DEVNULL)
     return os.path.join(HERE, "_ref")
 
 

@@ -106,7 +106,9 @@ def test_ragged_knapsack_and_zero_row(fb):
     b[4] = 0
     mo, md = O.OracleGSO(b), fb.MatGSO(b)
     for t in range(3):
-        assert mo.update_gso_row(t, t) and md.update_gso_row(t, t).all()
+        # catastrophic cancellation on the raw knapsack basis may make r(1,1) == 0 and the next row fail with a
+        # non-finite mu: whatever the reference's arithmetic does, the device must do the same
+        assert mo.update_gso_row(t, t) == bool(md.update_gso_row(t, t)[0])
     H.assert_state_equal(H.lattice_state(md.state(), 0), mo.state(), "partial discovery")
     mo.move_row(1, 9)
     md.move_row(1, 9)
