@@ -115,14 +115,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="lattices per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="lattices per GPU (0 = two full waves of the update kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("batched {row_op_end(%d,%d); update_gso_row(%d,%d)} on %d independent dim-%d (%dx%d) int64 lattices per GPU"
-                % (KAPPA, KAPPA + 1, KAPPA, KAPPA, a.batch, D, D, N_COLS))
+    def workload_str(nb):
+        return ("batched {row_op_end(%d,%d); update_gso_row(%d,%d)} on %s independent dim-%d (%dx%d) int64 lattices "
+                "per GPU" % (KAPPA, KAPPA + 1, KAPPA, KAPPA, nb, D, D, N_COLS))
 
     if a.impl == "reference":
         if rank != 0:
@@ -134,16 +135,18 @@ def main():
         line = {"metric": METRIC, "value": ref["value"], "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload.replace("%d independent" % a.batch, "threads*4 private"),
+                "config": {"workload": workload_str("threads*4 private"),
                            "note": "reference fplll 5.5.0 CPU path (oracle/_ref), all host threads"},
                 "cpu_baseline": ref,
                 "e2e": {"value": ref["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
+    import ctypes as C
     import numpy as np
     import torch
     import fplll_b200 as fb
+    from fplll_b200.gso import _lib, _ck
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -153,11 +156,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = a.batch
+    if B <= 0:
+        # the resident-slot count depends on d, n (shared memory per warp): ask a handle of the real shape
+        hp = C.c_void_p()
+        _ck(_lib().b200gso_create(C.byref(hp), 1, D, N_COLS, fb.GSO_ROW_EXPO, local), "create")
+        B = 2 * int(_lib().b200gso_resident_lattices(hp))
+        _lib().b200gso_destroy(hp)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
     dev_b = torch.randint(-(1 << 20), 1 << 20, (B, D, N_COLS), dtype=torch.int64, device="cuda", generator=gen)
-    import ctypes as C
-    from fplll_b200.gso import _lib, _ck
     m = fb.MatGSO.__new__(fb.MatGSO)
     m.batch, m.d, m.n, m.flags, m.enable_row_expo = B, D, N_COLS, fb.GSO_ROW_EXPO, True
     m._h = C.c_void_p()
@@ -189,12 +196,16 @@ def main():
     kern_gbps = B * per_lat / (ms_update * 1e-3) / 1e9
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
+    # host buffers are pinned (cudaHostAlloc via torch): the C-ABI takes plain host pointers, pinned ones DMA directly
     rows = torch.randint(-(1 << 20), 1 << 20, (B, N_COLS), dtype=torch.int64).pin_memory().numpy()
+    out = (torch.empty((B, D), dtype=torch.float64).pin_memory().numpy(),
+           torch.empty((B, D), dtype=torch.float64).pin_memory().numpy(),
+           torch.empty((B,), dtype=torch.int32).pin_memory().numpy())
     def e2e_step():
-        m.upload_row(KAPPA, rows)          # H2D B*n*8 + row_op_end
-        ok = m.update_gso_row(KAPPA)       # D2H B*4
-        mu, r, v = m.get_mu_r_row(KAPPA)   # D2H 2*B*d*8 + B*4
-        return ok
+        m.upload_row(KAPPA, rows)                    # H2D B*n*8, then write b[kappa] + row_op_end(kappa,kappa+1)
+        m.update_gso_row(KAPPA, want_ok=False)       # stream-ordered
+        mu, r, v = m.get_mu_r_row(KAPPA, out=out)    # D2H 2*B*d*8 + B*4, synchronises
+        return v
     for _ in range(a.warmup):
         e2e_step()
     if dist:
@@ -202,24 +213,24 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        ok = e2e_step()
+        v = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert ok.all()
+    assert (v == KAPPA + 1).all()  # every lattice's row kappa is valid through the diagonal
     if dist:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_val = world * B * per_lat * a.steps / e2e_s / 1e9
     h2d = B * N_COLS * 8
-    d2h = 2 * B * D * 8 + 2 * B * 4
+    d2h = 2 * B * D * 8 + B * 4
 
     if rank == 0:
         peak, peak_src = peaks()
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "entries": "uniform int in [-2^20, 2^20)", "flags": "GSO_ROW_EXPO",
+                "config": {"workload": workload_str(B), "batch": B, "entries": "uniform int in [-2^20, 2^20)", "flags": "GSO_ROW_EXPO",
                            "state_bytes_per_gpu": int(B * 1.39e6), "l2": "inputs larger than L2 (state >> 126 MB)",
                            "algorithmic_bytes_per_lattice": per_lat},
                 "roofline": {"bound": "hbm", "kernel": "k_update_row (update_gso_row, g=1)", "achieved": kern_gbps,

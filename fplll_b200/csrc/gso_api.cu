@@ -29,15 +29,17 @@ thread_local std::string g_err;
     }                                                                                              \
   } while (0)
 
+template <bool FULL_SMEM = true>
 __device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *&lov, int &lane)
 {
   extern __shared__ __align__(16) double smem[];
   const int w = threadIdx.x >> 5;
   lane        = threadIdx.x & 31;
   const int l = blockIdx.x * (blockDim.x >> 5) + w;
-  const size_t per = WarpSmem::doubles(S.d, S.n) + (size_t)((S.d + 2 + 1) & ~1);
-  s.carve(smem + (size_t)w * per, S.d, S.n);
-  lov = smem + (size_t)w * per + WarpSmem::doubles(S.d, S.n);
+  const size_t base = WarpSmem::doubles(S.d, S.n, FULL_SMEM);
+  const size_t per  = base + (FULL_SMEM ? (size_t)((S.d + 2 + 1) & ~1) : 0);
+  s.carve(smem + (size_t)w * per, S.d, S.n, FULL_SMEM);
+  lov = FULL_SMEM ? smem + (size_t)w * per + base : nullptr;
   if (l >= S.B)
     return false;
   v = S.view(l);
@@ -109,13 +111,14 @@ __global__ void k_discover_all(Batch S)
     warp_discover_row(v, lane);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_update_row(Batch S, int i, int last_j, int *ok)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_update_row(Batch S, int i, int last_j, int *ok)
 {
   View v;
   WarpSmem s;
   double *lov;
   int lane;
-  if (!warp_setup(S, v, s, lov, lane))
+  if (!warp_setup<false>(S, v, s, lov, lane))
     return;
   const bool r = warp_update_gso_row(v, i, last_j, s, lane);
   if (ok && lane == 0)
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_update_gso(Batch S, int 
   WarpSmem s;
   double *lov;
   int lane;
-  if (!warp_setup(S, v, s, lov, lane))
+  if (!warp_setup<false>(S, v, s, lov, lane))
     return;
   bool r = true;
   for (int i = 0; i < v.d && r; i++)
@@ -197,6 +200,8 @@ __global__ void k_set_r(Batch S, int i, int j, const double *f)
   {
     View v              = S.view(l);
     v.r[tri_off(i) + j] = f[l];
+    if (i == j)
+      v.mu[mu_off(i, i)] = f[l];  // diagonal mirror (gso_layout.cuh)
     if (v.valid[i] == j)
       v.valid[i] = j + 1;
   }
@@ -242,7 +247,7 @@ __global__ void k_unpack_state(Batch S, double *mu, double *r, double *gf, doubl
     }
 }
 
-__global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row)
+__global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row, int *valid)
 {
   const int l = blockIdx.x;
   View v      = S.view(l);
@@ -253,6 +258,8 @@ __global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row)
     if (r_row)
       r_row[(size_t)l * S.d + j] = (j <= i) ? v.r[tri_off(i) + j] : 0.0;
   }
+  if (valid && threadIdx.x == 0)
+    valid[l] = v.valid[i];
 }
 
 template <int MAXQ>
@@ -285,14 +292,40 @@ struct b200gso
   Batch S;
   int device;
   cudaStream_t stream;
-  size_t smem_bytes;
+  size_t smem_bytes, smem_compact;
   int *d_ok;      // batch ints
   double *d_tmp;  // batch doubles
   long *d_ltmp;   // batch longs
+  int64_t *d_rows;    // batch*n   (upload_row staging)
+  double *d_rowbuf;   // 2*batch*d (get_mu_r_row staging)
+  int *d_valid_i;     // batch
   std::vector<void *> allocs;
 };
 
+static int upd_variant()
+{
+  static int v = -1;
+  if (v < 0)
+  {
+    const char *e = getenv("B200_UPD_MINB");  // tuning knob for experiments: CTAs/SM the update kernel is compiled for
+    v             = e ? atoi(e) : 5;
+  }
+  return v;
+}
+static int grid_warps(const b200gso *h);
+static void launch_update_row(b200gso *h, int i, int last_j);
 static int grid_warps(const b200gso *h) { return (h->S.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+
+static void launch_update_row(b200gso *h, int i, int last_j)
+{
+  const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
+  switch (upd_variant())
+  {
+  case 5: k_update_row<5><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
+  case 6: k_update_row<6><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
+  default: k_update_row<8><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
+  }
+}
 
 template <class T> static int dev_alloc(b200gso *h, T **p, size_t count)
 {
@@ -337,6 +370,13 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
     return B200GSO_ENODEV;
   }
   CK(cudaSetDevice(device));
+  {
+    // L2 -> DRAM fetch granularity hint.  The panel sweeps issue whole 256-byte lines, but the partial last panel,
+    // the diagonal tiles and the scattered mu(i,.) row write touch single 32-byte sectors; at the default (128 B)
+    // those cost 9 % extra DRAM traffic (profiles/r1_update_row_v2*.txt).  B200_L2_FETCH overrides (32/64/128).
+    const char *e = getenv("B200_L2_FETCH");
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, e ? (size_t)atoi(e) : (size_t)32);
+  }
   b200gso *h = new b200gso();
   h->device  = device;
   Batch &S   = h->S;
@@ -360,6 +400,9 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   rc |= dev_alloc(h, &h->d_ok, (size_t)batch);
   rc |= dev_alloc(h, &h->d_tmp, (size_t)batch);
   rc |= dev_alloc(h, &h->d_ltmp, (size_t)batch * 4);
+  rc |= dev_alloc(h, &h->d_rows, (size_t)batch * n);
+  rc |= dev_alloc(h, &h->d_rowbuf, (size_t)2 * batch * d);
+  rc |= dev_alloc(h, &h->d_valid_i, (size_t)batch);
   if (rc)
   {
     for (void *p : h->allocs)
@@ -369,13 +412,14 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->smem_bytes = WARPS_PER_CTA * (WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1)) * sizeof(double);
+  h->smem_compact = WARPS_PER_CTA * WarpSmem::doubles(d, n, false) * sizeof(double);
   if (h->smem_bytes > 227 * 1024)
   {
     g_err = "b200gso_create: d/n too large for the per-warp shared-memory scratch";
     b200gso_destroy(h);
     return B200GSO_EINVAL;
   }
-  const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row,
+  const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row<8>, (const void *)k_update_row<6>, (const void *)k_update_row<5>,
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
                        (const void *)k_lll<4>,       (const void *)k_lll<8>,       (const void *)k_lll<16>};
@@ -462,12 +506,10 @@ int b200gso_upload_row(b200gso_t *h, int i, const int64_t *rows)
   if (!h || !rows || i < 0 || i >= h->S.d)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  const size_t cnt = (size_t)h->S.B * h->S.n;
-  int64_t *tmp     = nullptr;
-  CK(cudaMallocAsync(&tmp, cnt * sizeof(int64_t), h->stream));
-  CK(cudaMemcpyAsync(tmp, rows, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-  k_upload_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, tmp);
-  CK(cudaFreeAsync(tmp, h->stream));
+  // stream-ordered: with pinned `rows` this returns without waiting (the caller must not reuse `rows` before the
+  // next synchronising call); pageable memory makes cudaMemcpyAsync stage synchronously, which is also correct.
+  CK(cudaMemcpyAsync(h->d_rows, rows, (size_t)h->S.B * h->S.n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  k_upload_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, h->d_rows);
   CK(cudaGetLastError());
   return 0;
 }
@@ -498,7 +540,7 @@ int b200gso_update_gso_row(b200gso_t *h, int i, int last_j, int *ok)
   if (!h || i < 0 || i >= h->S.d || last_j < 0 || last_j > i)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  k_update_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, last_j, h->d_ok);
+  launch_update_row(h, i, last_j);
   return fetch_ok(h, ok);
 }
 
@@ -507,7 +549,7 @@ int b200gso_update_gso(b200gso_t *h, int *ok)
   if (!h)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, h->d_ok);
+  k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_compact, h->stream>>>(h->S, h->d_ok);
   return fetch_ok(h, ok);
 }
 
@@ -642,17 +684,15 @@ int b200gso_get_mu_r_row(b200gso_t *h, int i, double *mu_row, double *r_row, int
   CK(cudaSetDevice(h->device));
   const Batch &S   = h->S;
   const size_t cnt = (size_t)S.B * S.d;
-  double *t        = nullptr;
-  CK(cudaMallocAsync(&t, 2 * cnt * 8, h->stream));
-  k_get_row<<<S.B, 128, 0, h->stream>>>(S, i, mu_row ? t : nullptr, r_row ? t + cnt : nullptr);
+  double *t        = h->d_rowbuf;
+  k_get_row<<<S.B, 128, 0, h->stream>>>(S, i, mu_row ? t : nullptr, r_row ? t + cnt : nullptr,
+                                        valid ? h->d_valid_i : nullptr);
   if (mu_row)
     CK(cudaMemcpyAsync(mu_row, t, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
   if (r_row)
     CK(cudaMemcpyAsync(r_row, t + cnt, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
   if (valid)
-    CK(cudaMemcpy2DAsync(valid, sizeof(int), S.valid + i, (size_t)S.d * sizeof(int), sizeof(int), S.B,
-                         cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaFreeAsync(t, h->stream));
+    CK(cudaMemcpyAsync(valid, h->d_valid_i, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;
@@ -706,7 +746,7 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
     else
       k_invalidate_gso_row<<<(h->S.B + 127) / 128, 128, 0, h->stream>>>(h->S, i);
     CK(cudaEventRecord(ev[2 * r], h->stream));
-    k_update_row<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, i, h->d_ok);
+    launch_update_row(h, i, i);
     CK(cudaEventRecord(ev[2 * r + 1], h->stream));
   }
   CK(cudaEventRecord(ev[2 * reps + 1], h->stream));
@@ -728,6 +768,20 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
     *ms_total = all;
   CK(cudaGetLastError());
   return 0;
+}
+
+int b200gso_resident_lattices(b200gso_t *h)
+{
+  if (!h)
+    return B200GSO_EINVAL;
+  cudaSetDevice(h->device);
+  int nb = 0, sms = 0;
+  const int v = upd_variant();
+  const void *f = v == 6 ? (const void *)k_update_row<6> : v == 8 ? (const void *)k_update_row<8> : (const void *)k_update_row<5>;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, h->smem_compact) != cudaSuccess)
+    return B200GSO_ECUDA;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  return nb * sms * WARPS_PER_CTA;
 }
 
 int b200gso_sync(b200gso_t *h)

@@ -15,6 +15,8 @@
 //   mu  : packed LOWER TRIANGLE of panels — panel p keeps columns 0 .. 32(p+1)-1 only
 //         (base 512*p*(p+1) doubles, element (j,k) at base + 32*k + (j & 31)); the upper halves of the diagonal
 //         32x32 tiles are never read (loads are predicated) so DRAM traffic stays at the packed-triangle bytes.
+//         The otherwise unused slot mu(j,j) mirrors r(j,j): update_gso_row divides by it (gso_interface.cpp:155), and
+//         this way the divisor arrives with the diagonal tile's own lines instead of a 256-byte-strided gather.
 //   bf  : panel p keeps all n columns (base 32*n*p, element (j,c) at base + 32*c + (j & 31)).
 //
 //   r, gf : row-packed lower triangle including the diagonal, rows padded to an even length so every row

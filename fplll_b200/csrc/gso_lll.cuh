@@ -196,8 +196,7 @@ __device__ inline double warp_get_gram_diag(const View &v, WarpSmem &s, int i, i
   if (val != val)
   {
     const int ncols = v.meta[M_NKC];
-    for (int c = lane; c < ncols; c += 32)
-      s.vb[c] = v.bf[bf_off(i, c, v.n)];
+    warp_stage_bf_row(v, i, ncols, s.vb, lane);
     __syncwarp();
     if (lane == 0)
     {

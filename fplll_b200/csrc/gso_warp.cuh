@@ -13,19 +13,22 @@ namespace b200 {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// per-warp shared-memory scratch (doubles): vb[n] | rrow[dpad] | murow[dpad] | aux[dpad] | xs[dpad]
+// per-warp shared-memory scratch (doubles).  full: vb[n] | rrow | murow | aux | xs  (LLL / Babai);
+// compact (update_gso_row only): vb[n] | rrow | murow, aux aliases murow (the diagonal product is formed in place).
 struct WarpSmem
 {
   double *vb, *rrow, *murow, *aux, *xs;
-  __host__ __device__ static size_t doubles(int d, int n)
+  __host__ __device__ static size_t doubles(int d, int n, bool full = true)
   {
     int dpad = (d + 32 + 1) & ~1, npad = (n + 1) & ~1;
-    return (size_t)npad + 4 * (size_t)dpad;
+    return (size_t)npad + (full ? 4 : 2) * (size_t)dpad;
   }
-  __device__ void carve(double *base, int d, int n)
+  __device__ void carve(double *base, int d, int n, bool full = true)
   {
     int dpad = (d + 32 + 1) & ~1, npad = (n + 1) & ~1;
-    vb = base, rrow = vb + npad, murow = rrow + dpad, aux = murow + dpad, xs = aux + dpad;
+    vb = base, rrow = vb + npad, murow = rrow + dpad;
+    aux = full ? murow + dpad : murow;
+    xs  = full ? aux + dpad : nullptr;
   }
 };
 
@@ -113,25 +116,77 @@ __device__ inline void warp_discover_row(const View &v, int lane)
   __syncwarp();
 }
 
-// Sequential dot product of rows i and j of bf over [0,ncols) — numvect.h:385-395 — executed redundantly by the
-// lanes that need it (each lane its own j).  vb = bf_i staged in shared memory.
+// Stage bf(i, 0..ncols) in shared memory.  Row i of bf is a 256-byte-strided gather in the panel layout, so it is
+// re-derived from the contiguous int64 row instead: update_bf (gso.cpp:24-48) stores frexp/ldexp of (double)b(i,c),
+// which is exactly (double)b(i,c) * 2^-row_expo[i] (power-of-two scaling is exact), hence bit-identical.
+// Precondition (the reference's !in_row_op_range(i) assert, gso.h:316): row_op_end has run since b[i] last changed.
+__device__ inline void warp_stage_bf_row(const View &v, int i, int ncols, double *vb, int lane)
+{
+  const int64_t *brow = v.b + (size_t)i * v.ldb;
+  const int e         = v.row_expo_en ? -v.row_expo[i] : 0;
+  for (int c = lane; c < ncols; c += 32)
+    vb[c] = ldexp((double)brow[c], e);
+}
+
+// One lane's ordered chain  acc = acc (+|-) col[k] * vec[k]  for k = k0 .. k1-1 (ascending, two roundings per step):
+// the inner loop of both dot_product (numvect.h:385-395, SUB=false) and update_gso_row (gso_interface.cpp:147-151,
+// SUB=true).  col points at this lane's row inside a panel (consecutive k are 32 doubles apart, so a warp-wide load
+// is one 256-byte line); vec lives in shared memory.  Loads are double-buffered 8 deep: the kernel is bound by HBM
+// latency x bytes in flight (profiles/), so the next group is always requested before the current one is consumed.
+template <bool SUB>
+__device__ inline double lane_chain(double acc, const double *__restrict__ col, const double *vec, int k0, int k1)
+{
+  const int ng = (k1 - k0) >> 3;
+  double x[8], y[8];
+  if (ng > 0)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      x[u] = col[(size_t)(k0 + u) * 32];
+  }
+  for (int g = 0; g < ng; g += 2)
+  {
+    const int k = k0 + 8 * g;
+    if (g + 1 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        y[u] = col[(size_t)(k + 8 + u) * 32];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+    {
+      const double t = __dmul_rn(x[u], vec[k + u]);
+      acc            = SUB ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+    }
+    if (g + 2 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        x[u] = col[(size_t)(k + 16 + u) * 32];
+    }
+    if (g + 1 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+      {
+        const double t = __dmul_rn(y[u], vec[k + 8 + u]);
+        acc            = SUB ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+      }
+    }
+  }
+  for (int k = k0 + 8 * ng; k < k1; k++)
+  {
+    const double t = __dmul_rn(col[(size_t)k * 32], vec[k]);
+    acc            = SUB ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  }
+  return acc;
+}
+
+// dot_product(bf_i, bf_j) over [0,ncols), numvect.h:385-395: first term a bare product, then the ordered chain.
 __device__ inline double lane_dot(const double *__restrict__ bfcol /* &bf(j,0) */, const double *vb, int ncols)
 {
-  double acc = __dmul_rn(bfcol[0], vb[0]);
-  int c      = 1;
-  for (; c + 8 <= ncols; c += 8)
-  {
-    double x[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      x[u] = bfcol[(size_t)(c + u) * 32];
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      acc = __dadd_rn(acc, __dmul_rn(x[u], vb[c + u]));
-  }
-  for (; c < ncols; c++)
-    acc = __dadd_rn(acc, __dmul_rn(bfcol[(size_t)c * 32], vb[c]));
-  return acc;
+  return lane_chain<false>(__dmul_rn(bfcol[0], vb[0]), bfcol, vb, 1, ncols);
 }
 
 // MatGSOInterface::update_gso_row(i, last_j), gso_interface.cpp:131-164, with get_gram (gso.h:314-331) inlined.
@@ -155,8 +210,7 @@ __device__ inline bool warp_update_gso_row(const View &v, int i, int last_j, War
     anyn |= (gfrow[j] != gfrow[j]);
   anyn = __any_sync(FULL, anyn);
   if (anyn)
-    for (int c = lane; c < ncols; c += 32)
-      s.vb[c] = v.bf[bf_off(i, c, n)];
+    warp_stage_bf_row(v, i, ncols, s.vb, lane);
   for (int k = lane; k < j0; k += 32)
     s.rrow[k] = rrow_g[k];
   __syncwarp();
@@ -181,42 +235,49 @@ __device__ inline bool warp_update_gso_row(const View &v, int i, int last_j, War
     else if (j < j0)
       acc = s.rrow[j];  // already-valid r(i,j): only broadcast in the triangle below
     const double *mup = v.mu + mu_panel_base(p) + lane;
+    double rd         = 1.0;  // r(j,j), read from the mu(j,j) slot of the diagonal tile (see gso_layout.cuh)
     // rectangular part: columns k < 32p, all r(i,k) already in shared memory
     if (act)
+      acc = lane_chain<true>(acc, mup, s.rrow, 0, 32 * p);
+    // triangular part: column 32p+t is final in lane t once steps 0..t-1 are applied.  4 chunks of 8 columns,
+    // the next chunk's tile entries are requested while the current chunk's shuffle chain runs.
     {
-      const int kend = 32 * p;
-      int k          = 0;
-      for (; k + 8 <= kend; k += 8)
+      const double *tile = mup + (size_t)(32 * p) * 32;
+      double m[8], mn[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        m[u] = (act && lane >= u) ? tile[(size_t)u * 32] : 0.0;  // lane == u picks up its diagonal r(j,j) mirror
+#pragma unroll
+      for (int q = 0; q < 4; q++)
       {
-        double m[8];
+        if (q < 3)
+        {
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            mn[u] = (act && lane >= 8 * (q + 1) + u) ? tile[(size_t)(8 * (q + 1) + u) * 32] : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          m[u] = mup[(size_t)(k + u) * 32];
+        {
+          const int t = 8 * q + u;
+          if (lane == t)
+            rd = m[u];
+          if (t < 31)
+          {
+            const double rk = __shfl_sync(FULL, acc, t);
+            if (act && lane > t)
+              acc = __dsub_rn(acc, __dmul_rn(m[u], rk));
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          acc = __dsub_rn(acc, __dmul_rn(m[u], s.rrow[k + u]));
-      }
-    }
-    // triangular part: column 32p+t is final in lane t once steps 0..t-1 are applied
-    {
-      double m[32];
-      const bool ld = act;
-#pragma unroll
-      for (int t = 0; t < 32; t++)
-        m[t] = (ld && lane > t) ? mup[(size_t)(32 * p + t) * 32] : 0.0;
-#pragma unroll
-      for (int t = 0; t < 31; t++)
-      {
-        const double rk = __shfl_sync(FULL, acc, t);
-        if (act && lane > t)
-          acc = __dsub_rn(acc, __dmul_rn(m[t], rk));
+          m[u] = mn[u];
       }
     }
     if (act)
     {
       rrow_g[j]       = acc;
       s.rrow[j]       = acc;
-      const double rd = v.r[tri_off(j) + j];
       const double mm = __ddiv_rn(acc, rd);
       v.mu[mu_off(i, j)] = mm;
       s.murow[j]      = mm;
@@ -243,9 +304,6 @@ __device__ inline bool warp_update_gso_row(const View &v, int i, int last_j, War
       double g = gfrow[i];
       if (g != g)
       {
-        if (!anyn)  // vb not staged (cannot happen: gf(i,i) NaN implies anyn) — keep for safety
-          for (int c = 0; c < ncols; c++)
-            s.vb[c] = v.bf[bf_off(i, c, n)];
         g = __dmul_rn(s.vb[0], s.vb[0]);
         for (int c = 1; c < ncols; c++)
           g = __dadd_rn(g, __dmul_rn(s.vb[c], s.vb[c]));
@@ -254,7 +312,8 @@ __device__ inline bool warp_update_gso_row(const View &v, int i, int last_j, War
       double acc = g;
       for (int k = 0; k < i; k++)
         acc = __dsub_rn(acc, s.aux[k]);
-      rrow_g[i] = acc;
+      rrow_g[i]          = acc;
+      v.mu[mu_off(i, i)] = acc;  // diagonal mirror
     }
     __syncwarp();
   }
@@ -493,6 +552,8 @@ __device__ inline void warp_set_r(const View &v, int i, int j, double f, int lan
   if (lane == 0)
   {
     v.r[tri_off(i) + j] = f;
+    if (i == j)
+      v.mu[mu_off(i, i)] = f;  // diagonal mirror
     if (v.valid[i] == j)
       v.valid[i] = j + 1;
   }

@@ -43,6 +43,7 @@ def _lib():
         L.b200gso_lll.argtypes = [vp, C.c_double, C.c_double, ip, lp]
         L.b200gso_time_update_row.argtypes = [vp, i, i, i, _P(C.c_float), _P(C.c_float)]
         L.b200gso_sync.argtypes = [vp]
+        L.b200gso_resident_lattices.argtypes = [vp]
         _sig_done = True
     return L
 
@@ -82,10 +83,14 @@ class MatGSO:
     def discover_all_rows(self):
         _ck(_lib().b200gso_discover_all_rows(self._h), "discover_all_rows")
 
-    def update_gso_row(self, i, last_j=None):
+    def update_gso_row(self, i, last_j=None, want_ok=True):
+        """update_gso_row(i, last_j) -> bool per lattice.  want_ok=False skips the read-back (stream-ordered, no sync)."""
+        lj = i if last_j is None else last_j
+        if not want_ok:
+            _ck(_lib().b200gso_update_gso_row(self._h, i, lj, None), "update_gso_row")
+            return None
         ok = np.zeros(self.batch, np.int32)
-        _ck(_lib().b200gso_update_gso_row(self._h, i, i if last_j is None else last_j, _ptr(ok, C.c_int)),
-            "update_gso_row")
+        _ck(_lib().b200gso_update_gso_row(self._h, i, lj, _ptr(ok, C.c_int)), "update_gso_row")
         return ok.astype(bool)
 
     def update_gso(self):
@@ -142,9 +147,12 @@ class MatGSO:
                     n_known_rows=meta[:, 0].copy(), n_known_cols=meta[:, 1].copy(),
                     n_source_rows=meta[:, 2].copy(), b=self.b)
 
-    def get_mu_r_row(self, i):
-        mu, r = np.empty((self.batch, self.d)), np.empty((self.batch, self.d))
-        v = np.empty(self.batch, np.int32)
+    def get_mu_r_row(self, i, out=None):
+        """rows i of mu and r and gso_valid_cols[i] for every lattice.  out=(mu, r, valid) reuses caller buffers
+        (pinned host memory makes the copies asynchronous DMA)."""
+        if out is None:
+            out = (np.empty((self.batch, self.d)), np.empty((self.batch, self.d)), np.empty(self.batch, np.int32))
+        mu, r, v = out
         _ck(_lib().b200gso_get_mu_r_row(self._h, i, _ptr(mu, C.c_double), _ptr(r, C.c_double), _ptr(v, C.c_int)),
             "get_mu_r_row")
         return mu, r, v
@@ -169,6 +177,9 @@ class MatGSO:
         _ck(_lib().b200gso_time_update_row(self._h, i, reps, 1 if invalidate else 0, C.byref(ms), C.byref(tot)),
             "time_update_row")
         return ms.value, tot.value
+
+    def resident_lattices(self):
+        return int(_lib().b200gso_resident_lattices(self._h))
 
     def sync(self):
         _ck(_lib().b200gso_sync(self._h), "sync")

@@ -106,6 +106,10 @@ int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats
  * launch), *ms_total = device time of the whole region (all 2*reps launches).  Either pointer may be NULL. */
 int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float *ms_update_mean, float *ms_total);
 
+/* Number of lattices the update_gso_row kernel keeps resident at once on this device (SMs x CTAs/SM x warps/CTA):
+ * batches that are a multiple of it run in full waves.  Negative on error. */
+int b200gso_resident_lattices(b200gso_t *h);
+
 /* Synchronise the handle's stream (all calls above are stream-ordered on one stream per handle). */
 int b200gso_sync(b200gso_t *h);
 
