@@ -1,0 +1,78 @@
+/* b200enum.h — C-ABI of the B200-native lattice enumerator (the BKZ SVP subtree search).
+ *
+ * Drop-in boundary: fplll's external-enumerator hook.  The reference calls a process-wide
+ *   std::function<extenum_fc_enumerate>  (fplll/enum/enumerate_ext_api.h:88-92, installed with
+ *   set_external_enumerator(), fplll/enum/enumerate_ext.h:100) from Enumeration::enumerate (enum/enumerate.h:87-111)
+ * handing it `dim`, the normalised `maxdist`, and three callbacks (set_config / process_sol / process_subsol).
+ * std::function cannot cross a C ABI, so b200enum_run below is the C core with exactly that information flattened to
+ * plain pointers, and INTEGRATION.md shows the 30-line C++ adapter with the typedef'd signature that a maintainer
+ * registers through set_external_enumerator (fplll_b200/csrc/fplll_extenum_adapter.cpp).
+ *
+ * Scope: SVP, primal, no sub-solutions — what BKZ's svp_reduction asks for
+ * (bkz.cpp:329-331 with FastEvaluator(1) — bkz.h:324).  dual / findsubsols requests are answered with
+ * B200ENUM_UNSUPPORTED so the adapter returns nodes[0] = ~0 and fplll falls back (enumerate_ext.cpp:88), exactly
+ * like the bundled enumlib does for dual (enum-parallel/enumlib.cpp:98-104).
+ */
+#ifndef B200ENUM_H
+#define B200ENUM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ENUM_MAX_DIM 160
+
+#define B200ENUM_OK 0
+#define B200ENUM_EINVAL (-1)
+#define B200ENUM_ENODEV (-2)
+#define B200ENUM_ECUDA (-3)
+#define B200ENUM_UNSUPPORTED (-5)
+#define B200ENUM_EOVERFLOW (-6) /* more improving solutions in one wave than the device buffer holds */
+
+/* flags */
+#define B200ENUM_FIXED_RADIUS 1 /* never shrink the radius: counts every leaf inside it (known-answer tests) */
+#define B200ENUM_DUAL 2         /* request flags of the hook; both are declined */
+#define B200ENUM_FINDSUBSOLS 4
+
+/* extenum_cb_process_sol (enumerate_ext_api.h:62-63): gets the squared length and the coefficient vector of a new
+ * solution, returns the new enumeration bound. */
+typedef double (*b200enum_sol_cb)(void *ctx, double dist, const double *sol);
+
+typedef struct
+{
+  uint64_t host_nodes;   /* nodes visited by the host breadth phase (top levels) */
+  uint64_t device_nodes; /* nodes visited by the GPU subtree walkers */
+  uint64_t leaves;       /* FIXED_RADIUS: number of non-zero leaves inside the radius (this shard) */
+  int top_levels;        /* T: levels expanded on the host */
+  int n_roots;           /* subtree roots handed to the GPU(s) (all shards) */
+  int n_solutions;       /* improving solutions replayed through the callback */
+  int n_devices;
+  int n_rounds;          /* kernel rounds (budgeted walk + work split) */
+  double final_maxdist;
+  float device_ms; /* max over devices of the kernel time (CUDA events on the launching streams) */
+} b200enum_stats;
+
+/* Enumerate { x in Z^dim, x != 0 :  sum_k rdiag[k] * (x_k + sum_{j>k} mut[k*dim+j] * x_j)^2  <=  pruning[k]-bounded
+ * partial sums of maxdist }  in Schnorr-Euchner order (enum/enumerate_base.cpp:152-254).
+ *   mut      dim*dim, row-major, mut[k*dim+j] = mu(j,k) for j > k — the `mutranspose=true` layout the hook's set_config
+ *            callback fills (enumerate_ext.cpp:108-121); rdiag, pruning: dim each (pruning may be NULL = all ones);
+ *            all normalised by 2^-normexp by the caller, as ExternalEnumeration::enumerate does (enumerate_ext.cpp:64-79)
+ *   devices  ndev CUDA ordinals driven from this process (NULL = {0}); subtree roots are dealt round-robin
+ *   shard_rank/shard_world  additionally restrict this call to roots r with r % shard_world == shard_rank — used when
+ *            one process per GPU cooperates (torch.distributed): every rank calls with the same inputs and exchanges
+ *            (dist, sol) afterwards.  Use 0/1 otherwise.
+ *   cb       called on the host, in order of improvement, for every solution that lowered the radius (FastEvaluator
+ *            "best 1" semantics, enum/evaluator.h:122-156); may be NULL
+ *   nodes    dim counters (per level, like the array the hook returns), may be NULL
+ * Returns B200ENUM_OK or a negative code.  There is no CPU fallback: without a device -> B200ENUM_ENODEV. */
+int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag, const double *pruning, int flags,
+                 const int *devices, int ndev, int shard_rank, int shard_world, b200enum_sol_cb cb, void *ctx,
+                 uint64_t *nodes, b200enum_stats *stats);
+
+const char *b200enum_last_error(void);
+int b200enum_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -231,3 +231,56 @@ class RefSession:
         out = run_ref("\n".join(self.lines) + "\n")
         recs = read_dumps(self.dump) if os.path.exists(self.dump) else []
         return out, recs
+
+
+# ---- enumeration ----------------------------------------------------------------------------------------
+
+def enum_svp(mut, rdiag, pruning, maxdist, shrink=True):
+    """oracle/enum_oracle.c::oenum_svp.  Returns dict(nsols, best, sol, nodes)."""
+    L = lib()
+    d = len(rdiag)
+    mut = np.ascontiguousarray(mut, np.float64).reshape(d, d)
+    rdiag = np.ascontiguousarray(rdiag, np.float64)
+    pr = None if pruning is None else np.ascontiguousarray(pruning, np.float64)
+    sol = np.zeros(d)
+    best = C.c_double()
+    nodes = np.zeros(d, np.uint64)
+    L.oenum_svp.restype = C.c_long
+    L.oenum_svp.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                            C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                            C.POINTER(C.c_uint64)]
+    n = L.oenum_svp(d, mut.ctypes.data_as(C.POINTER(C.c_double)), rdiag.ctypes.data_as(C.POINTER(C.c_double)),
+                    pr.ctypes.data_as(C.POINTER(C.c_double)) if pr is not None else None, float(maxdist),
+                    1 if shrink else 0, sol.ctypes.data_as(C.POINTER(C.c_double)), C.byref(best),
+                    nodes.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return dict(nsols=int(n), best=best.value, sol=sol, nodes=nodes)
+
+
+def read_enum_records(path):
+    """Parse the records ref_probe's `enum` appends (layout in oracle/ref_probe.cpp)."""
+    raw = open(path, "rb").read()
+    off, out = 0, []
+    while off < len(raw):
+        hdr = np.frombuffer(raw, np.int32, 4, off)
+        off += 16
+        assert hdr[0] == 0x454E554D
+        d, found, mode = int(hdr[1]), int(hdr[2]), int(hdr[3])
+        md, best = np.frombuffer(raw, np.float64, 2, off)
+        off += 16
+        normexp = int(np.frombuffer(raw, np.int64, 1, off)[0])
+        off += 8
+        sol = np.frombuffer(raw, np.float64, d, off).copy()
+        off += 8 * d
+        nodes = np.frombuffer(raw, np.uint64, d, off).copy()
+        off += 8 * d
+        rec = dict(d=d, found=found, mode=mode, maxdist=float(md), best=float(best), normexp=normexp, sol=sol,
+                   nodes=nodes)
+        if mode == 2:
+            rec["mut"] = np.frombuffer(raw, np.float64, d * d, off).reshape(d, d).copy()
+            off += 8 * d * d
+            rec["rdiag"] = np.frombuffer(raw, np.float64, d, off).copy()
+            off += 8 * d
+            rec["pruning"] = np.frombuffer(raw, np.float64, d, off).copy()
+            off += 8 * d
+        out.append(rec)
+    return out

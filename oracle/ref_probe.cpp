@@ -186,6 +186,114 @@ static void time_update_gso_mt(int reps, int threads, int per)
          (long)reps * threads * per, mx);
 }
 
+/* ---- enumeration probes -------------------------------------------------------------------------------
+ * enum FIRST LAST FACTOR PRUNEFILE OUT MODE : Enumeration<Z_NR<long>,FP_NR<double>>::enumerate on block
+ *   [FIRST,LAST) of the current long GSO with max_dist = FACTOR * r(FIRST,FIRST), pruning coefficients read from
+ *   PRUNEFILE ("-" = none).  MODE = internal (EnumerationDyn, enumerate.cpp:58) | enumlib (the bundled parallel
+ *   enumerator through the extenum hook) | capture (a hook that records exactly what the plugin API hands an
+ *   external enumerator — enumerate_ext.cpp:48-148 — and declines, so the internal enumerator then runs).
+ * OUT (binary, appended): int32 magic 0x454e554d, d, found, mode; f64 maxdist_norm (capture mode: as handed to the
+ *   hook, else -1), f64 best_dist (evaluator's, denormalised), int64 normexp; f64 sol[d]; u64 nodes[d];
+ *   capture mode only: f64 mut[d*d] (transposed layout of enumerate_ext.cpp:108-121), f64 rdiag[d], f64 pruning[d]
+ */
+struct EnumCapture
+{
+  int d         = 0;
+  double maxdist = -1;
+  vector<double> mut, rdiag, pruning;
+};
+static EnumCapture g_cap;
+
+static std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM>
+capture_enumerator(const int dim, fplll_extenum_enumf maxdist, std::function<extenum_cb_set_config> cbfunc,
+                   std::function<extenum_cb_process_sol>, std::function<extenum_cb_process_subsol>, bool, bool)
+{
+  g_cap.d       = dim;
+  g_cap.maxdist = maxdist;
+  g_cap.mut.assign((size_t)dim * dim, 0.0);
+  g_cap.rdiag.assign(dim, 0.0);
+  g_cap.pruning.assign(dim, 0.0);
+  cbfunc(g_cap.mut.data(), dim, true, g_cap.rdiag.data(), g_cap.pruning.data());
+  std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM> ret{};
+  ret[0] = ~uint64_t(0);  // "unsupported": fplll falls back to its own enumerator (enumerate_ext.cpp:88)
+  return ret;
+}
+
+static void run_enum(GsoL &m, int first, int last, double factor, const string &prunefile, const string &out,
+                     const string &mode)
+{
+  static std::function<extenum_fc_enumerate> bundled = get_external_enumerator();
+  int d = last - first;
+  vector<double> pr;
+  if (prunefile != "-")
+  {
+    ifstream f(prunefile);
+    double x;
+    while (f >> x)
+      pr.push_back(x);
+    if ((int)pr.size() != d)
+    {
+      fprintf(stderr, "pruning file has %d entries, need %d\n", (int)pr.size(), d);
+      exit(2);
+    }
+  }
+  int imode = 0;
+  if (mode == "internal")
+    set_external_enumerator(nullptr);
+  else if (mode == "enumlib")
+  {
+    set_external_enumerator(bundled);
+    imode = 1;
+  }
+  else
+  {
+    set_external_enumerator(capture_enumerator);
+    imode   = 2;
+    g_cap   = EnumCapture();
+  }
+  FastEvaluator<FP_NR<double>> ev;
+  Enumeration<Z_NR<long>, FP_NR<double>> en(m, ev);
+  long expo;
+  FP_NR<double> maxd = m.get_r_exp(first, first, expo);
+  maxd.mul(maxd, factor);
+  double t0 = now();
+  en.enumerate(first, last, maxd, expo, vector<FP_NR<double>>(), vector<enumxt>(), pr, false);
+  double sec = now() - t0;
+  set_external_enumerator(bundled);
+  FILE *f        = fopen(out.c_str(), "ab");
+  int found      = ev.empty() ? 0 : 1;
+  int32_t hdr[4] = {0x454e554d, d, found, imode};
+  wr(f, hdr, 4);
+  double md = imode == 2 ? g_cap.maxdist : -1.0;
+  wr(f, &md, 1);
+  double best = found ? ev.begin()->first.get_d() : -1.0;
+  wr(f, &best, 1);
+  int64_t ne = ev.normExp;
+  wr(f, &ne, 1);
+  vector<double> sol(d, 0.0);
+  if (found)
+    for (int i = 0; i < d; i++)
+      sol[i] = ev.begin()->second[i].get_d();
+  wr(f, sol.data(), d);
+  vector<uint64_t> nodes(d);
+  uint64_t tot = 0;
+  for (int i = 0; i < d; i++)
+  {
+    nodes[i] = en.get_nodes(i);
+    tot += nodes[i];
+  }
+  wr(f, nodes.data(), d);
+  if (imode == 2)
+  {
+    wr(f, g_cap.mut.data(), g_cap.mut.size());
+    wr(f, g_cap.rdiag.data(), d);
+    wr(f, g_cap.pruning.data(), d);
+  }
+  fclose(f);
+  printf("enum d=%d mode=%s found=%d best=%.17g nodes=%llu sec=%.6f\n", d, mode.c_str(), found, best,
+         (unsigned long long)tot, sec);
+}
+
 int main(int argc, char **argv)
 {
   string line;
@@ -200,7 +308,7 @@ int main(int argc, char **argv)
       puts("load P | save P | tolong | gso l|m FLAGS | update_gso | update_row I J | discover_all | "
            "row_addmul_we I J X E | row_op_begin F L | row_op_end F L | move_row O N | row_swap I J | "
            "set_r I J V | dump P | dumpb P | lll DELTA ETA METHOD FLOAT FLAGS | islll DELTA ETA | "
-           "time_update_row I REPS INV | time_update_row_mt I REPS T PER | time_update_gso_mt REPS T PER");
+           "enum FIRST LAST FACTOR PRUNEFILE OUT internal|enumlib|capture | set_threads T | time_update_row I REPS INV | time_update_row_mt I REPS T PER | time_update_gso_mt REPS T PER");
     }
     else if (c == "load")
     {
@@ -386,6 +494,25 @@ int main(int argc, char **argv)
       int ok = is_lll_reduced<Z_NR<mpz_t>, FP_NR<mpfr_t>>(M, delta, eta);
       FP_NR<mpfr_t>::set_prec(old);
       printf("islll %d\n", ok);
+    }
+    else if (c == "enum")
+    {
+      int first, last;
+      double factor;
+      string pf, out, mode;
+      is >> first >> last >> factor >> pf >> out >> mode;
+      if (!gl)
+      {
+        fprintf(stderr, "enum needs a long GSO\n");
+        return 2;
+      }
+      run_enum(*gl, first, last, factor, pf, out, mode);
+    }
+    else if (c == "set_threads")
+    {
+      int t;
+      is >> t;
+      printf("set_threads %d\n", set_threads(t));
     }
     else if (c == "time_update_row")
     {

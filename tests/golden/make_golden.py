@@ -89,6 +89,43 @@ def main():
                         n_known_rows=np.int32(rec["n_known_rows"]), n_known_cols=np.int32(rec["n_known_cols"]),
                         n_source_rows=np.int32(rec["n_source_rows"]),
                         mu_tril=rec["mu"][tl], r_tril=rec["r"][tl], gf_tril=rec["gf"][tl])
+    # --- enumeration fixtures (reference's internal enumerator through the plugin-API capture hook) ----------
+    import json
+    strat = json.load(open(os.path.join(O.REF_DIR, "strategies", "default.json")))
+    s60 = [e for e in strat if e["block_size"] == 60][0]
+    pr60 = s60["pruning_parameters"][15]   # [gh_factor = 1.05, coefficients, probability ~ 0.41]
+    prfile = os.path.join(TMP, "prune60.txt")
+    open(prfile, "w").write(" ".join(repr(float(c)) for c in pr60[1]))
+    out = os.path.join(TMP, "enum_fixture.bin")
+    if os.path.exists(out):
+        os.remove(out)
+    # radius as BKZ sets it (bkz.cpp:310-323): gh_factor * GH^2 of the block, expressed as a multiple of r(first,first)
+    import math
+    Rm = np.zeros((200, 200))
+    Rm[tl] = rec["r"][tl]
+    rii = np.array([Rm[i, i] * 2.0 ** (2 * int(rec["row_expo"][i])) for i in range(200)])
+
+    def gh_ratio(first, last):
+        n = last - first
+        gh2 = math.exp((2.0 / n) * math.lgamma(n / 2 + 1)) / math.pi * math.exp(np.sum(np.log(rii[first:last])) / n)
+        return gh2 / rii[first]
+    f100, f140 = float(1.05 * gh_ratio(100, 160)), float(1.05 * gh_ratio(140, 200))
+    script = ("load %s\ntolong\ngso l 2\nupdate_gso\n"
+              "enum 0 30 0.99 - %s capture\n"
+              "enum 100 160 %r %s %s capture\n"
+              "enum 140 200 %r %s %s capture\n") % (red_path, out, f100, prfile, out, f140, prfile, out)
+    print(O.run_ref(script, timeout=600))
+    recs = O.read_enum_records(out)
+    for name, r in zip(["enum_r200_b30_unpruned", "enum_r200_b60_pruned_100", "enum_r200_b60_pruned_140"], recs):
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), mut=r["mut"], rdiag=r["rdiag"], pruning=r["pruning"],
+                            maxdist=np.float64(r["maxdist"]), normexp=np.int64(r["normexp"]),
+                            found=np.int32(r["found"]), best=np.float64(r["best"]), sol=r["sol"], nodes=r["nodes"],
+                            gh_factor=np.float64(pr60[0]))
+    # Leech lattice known-answer test (tests/test_enum.cpp:55-100): 196560 minimal vectors of squared norm 32
+    leech_in = "/root/reference/tests/lattices/example_list_cvp_in_lattice"
+    lo = os.path.join(TMP, "leech_lll.txt")
+    O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (leech_in, lo))
+    np.savez_compressed(os.path.join(HERE, "leech_lll.npz"), b=np.array(O.read_matrix(lo), dtype=np.int64))
     print("golden fixtures written to", HERE)
 
 

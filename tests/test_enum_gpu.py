@@ -1,0 +1,90 @@
+"""GPU parity tests of the device enumerator (through the C-ABI of include/b200enum.h) against the oracle, the
+reference dumps (tests/golden/enum_*.npz) and the Leech-lattice known answer."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import oracle as O
+from test_enum_oracle import gso_block
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def en():
+    from fplll_b200 import enum
+    return enum
+
+
+def test_unpruned_30_best_vector_equals_reference(en):
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    res = en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]))
+    assert res["solutions"], "no solution found"
+    dist, x = res["solutions"][-1]
+    assert dist * 2.0 ** int(z["normexp"]) == float(z["best"])  # identical best-vector norm (SURVEY §8d gate 3)
+    assert np.array_equal(x, z["sol"]) or np.array_equal(x, -z["sol"])
+    dists = [s[0] for s in res["solutions"]]
+    assert dists == sorted(dists, reverse=True)  # replayed in order of improvement
+
+
+def test_fixed_radius_node_counts_equal_oracle(en):
+    """with a fixed radius the visited node set is order-independent: per-level counts must be IDENTICAL."""
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    R = 0.55 * float(z["maxdist"])
+    ref = O.enum_svp(z["mut"], z["rdiag"], None, R, shrink=False)
+    res = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True)
+    assert np.array_equal(res["nodes"], ref["nodes"])
+    assert res["stats"]["leaves"] == ref["nsols"]
+    if ref["nsols"]:
+        assert res["solutions"][-1][0] == ref["best"]
+
+
+def test_leech_kissing_number(en):
+    """tests/test_enum.cpp:55-100: 196560 vectors of squared norm 32 inside radius 32.5 (each +-pair counted once)."""
+    b = H.gold("leech_lll.npz")["b"]
+    mut, rdiag = gso_block(b, 0, 24)
+    res = en.enumerate_svp(mut, rdiag, None, 32.5, fixed_radius=True)
+    assert res["stats"]["leaves"] == 196560 // 2
+    assert abs(res["solutions"][-1][0] - 32.0) < 1e-9
+    ref = O.enum_svp(mut, rdiag, None, 32.5, shrink=False)
+    assert np.array_equal(res["nodes"], ref["nodes"])
+
+
+def test_bkz60_block_without_solution_same_node_count_as_reference(en):
+    """BASELINE config #5 size: block [140,200) of the LLL-reduced r200 basis, strategies/default.json beta=60
+    pruning, radius 1.05 GH.  The reference finds nothing, so its radius never moves and its 561 045 742 visited
+    nodes (18 s on one core) are a full-size known answer: the device must visit exactly the same nodes."""
+    z = H.gold("enum_r200_b60_pruned_140.npz")
+    assert int(z["found"]) == 0
+    res = en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]))
+    assert not res["solutions"]
+    assert np.array_equal(res["nodes"], z["nodes"])
+    assert int(res["nodes"].sum()) == 561045742
+
+
+def test_bkz60_block_best_vector_equals_reference(en):
+    """block [100,160): the reference (3.2e9 nodes, 96 s on one core) finds a vector; same norm and same vector."""
+    z = H.gold("enum_r200_b60_pruned_100.npz")
+    res = en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]))
+    dist, x = res["solutions"][-1]
+    assert dist * 2.0 ** int(z["normexp"]) == float(z["best"])
+    assert np.array_equal(x, z["sol"]) or np.array_equal(x, -z["sol"])
+
+
+def test_shards_partition_the_tree(en):
+    """r % world == rank sharding (one process per GPU): the shards' node counts add up to the unsharded run."""
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    R = 0.5 * float(z["maxdist"])
+    full = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True)
+    parts = [en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True, shard=(r, 3)) for r in range(3)]
+    assert np.array_equal(sum(p["nodes"] for p in parts), full["nodes"])
+    assert sum(p["stats"]["leaves"] for p in parts) == full["stats"]["leaves"]
+
+
+def test_dual_and_subsols_are_declined_like_enumlib(en):
+    import fplll_b200 as fb
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    for fl in (en.DUAL, en.FINDSUBSOLS):
+        with pytest.raises(fb.B200Error) as e:
+            en.enumerate_svp(z["mut"], z["rdiag"], None, float(z["maxdist"]), flags=fl)
+        assert "(-5)" in str(e.value)

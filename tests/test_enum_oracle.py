@@ -1,0 +1,37 @@
+"""CPU tests (no GPU): the C restatement of the Schnorr-Euchner walk (oracle/enum_oracle.c) against dumps of the
+reference's own enumerator taken through its plugin API (tests/golden/enum_*.npz, made by make_golden.py) and the
+Leech-lattice known answer of the reference's tests/test_enum.cpp:55-100."""
+import numpy as np
+
+import helpers as H
+from oracle import oracle as O
+
+
+def gso_block(b, first, last):
+    """mut / rdiag of a basis block from the oracle GSO (no row_expo: true mu, r)."""
+    m = O.OracleGSO(b, 0)
+    assert m.update_gso()
+    s = m.state()
+    d = last - first
+    mut = np.zeros((d, d))
+    for k in range(d):
+        for j in range(k + 1, d):
+            mut[k, j] = s["mu"][first + j, first + k]
+    rdiag = np.array([s["r"][first + i, first + i] for i in range(d)])
+    return mut, rdiag
+
+
+def test_oracle_matches_reference_unpruned_30():
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    res = O.enum_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), shrink=True)
+    assert np.array_equal(res["nodes"], z["nodes"])  # per level, bit-identical pruning decisions
+    assert res["best"] * 2.0 ** int(z["normexp"]) == float(z["best"])
+    assert np.array_equal(res["sol"], z["sol"])
+
+
+def test_leech_kissing_number():
+    b = H.gold("leech_lll.npz")["b"]
+    mut, rdiag = gso_block(b, 0, 24)
+    res = O.enum_svp(mut, rdiag, None, 32.5, shrink=False)
+    assert res["nsols"] == 196560 // 2  # +-v counted once (SVP symmetry break, enumerate_base.h:145-171)
+    assert abs(res["best"] - 32.0) < 1e-9
