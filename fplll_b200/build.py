@@ -13,6 +13,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 TARGETS = {
     "libb200gso.so": ["gso_api.cu"],
     "libb200enum.so": ["enum_api.cu"],
+    "libb200bkz.so": ["gso_api.cu", "enum_api.cu", "bkz_api.cu"],
 }
 
 

@@ -19,8 +19,10 @@
 // of visited nodes — and therefore the node count — is identical to the reference's own enumerator.
 #include "../../include/b200enum.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <mutex>
@@ -413,6 +415,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
       return B200ENUM_EINVAL;
     }
   std::lock_guard<std::mutex> lock(g_mu);
+  const auto t_begin = std::chrono::steady_clock::now();
   const int d = dim;
   std::vector<double> prun(d, 1.0);
   if (pruning)
@@ -448,6 +451,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
   std::stable_sort(order.begin(), order.end(),
                    [&](unsigned a, unsigned b) { return br.rootdist[a] < br.rootdist[b]; });
 
+  const auto t_host = std::chrono::steady_clock::now();
   // ---- device depth phase ----
   const size_t cfg_n = (size_t)d * d + 2 * d;
   std::vector<double> cfg(cfg_n);
@@ -505,7 +509,9 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
   // rounds: every device works through its queue segment [head, tail); walkers that exhaust their node budget append
   // the unvisited parts as new tasks, which form the next round's segment.  The budget grows geometrically: small
   // first rounds multiply the parallelism quickly, later rounds amortise the launch.
-  unsigned budget = 64;
+  static const unsigned budget0 = getenv("B200_ENUM_BUDGET0") ? atoi(getenv("B200_ENUM_BUDGET0")) : 64;
+  static const unsigned budget_mul = getenv("B200_ENUM_BUDGET_MUL") ? atoi(getenv("B200_ENUM_BUDGET_MUL")) : 4;
+  unsigned budget = budget0;
   int rounds      = 0;
   const size_t smem = cfg_n * sizeof(double);
   for (;;)
@@ -532,7 +538,10 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
       a.A_bits = c->d_words, a.leaves = c->d_words + 2, a.nodes = c->d_nodes, a.sols = c->d_sols;
       a.fixed_radius = fixed ? 1 : 0;
       const size_t nt  = tail[q];
-      const int blocks = (int)std::max<size_t>(1, std::min<size_t>((nt + THREADS - 1) / THREADS, (size_t)c->sms * 4));
+      // resident walkers per SM: each keeps ~24 B x d of stacks in local memory; 2 CTAs x 128 walkers keep the whole
+      // working set in L1/L2 (4+ CTAs/SM spill the stacks to DRAM and run 5x slower)
+      static const int bpsm = getenv("B200_ENUM_BLOCKS_PER_SM") ? atoi(getenv("B200_ENUM_BLOCKS_PER_SM")) : 2;
+      const int blocks = (int)std::max<size_t>(1, std::min<size_t>((nt + THREADS - 1) / THREADS, (size_t)c->sms * bpsm));
       if (d <= 64)
         k_enum<64><<<blocks, THREADS, smem, c->stream>>>(a);
       else
@@ -551,7 +560,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
       CKE(cudaGetLastError());
       tail[q] = std::min<unsigned>(*(unsigned *)(c->h_words + 4), TASK_CAP);
     }
-    budget = std::min<unsigned>(budget * 4, 16384);
+    budget = std::min<unsigned>(budget * budget_mul, 16384);
     rounds++;
   }
   std::vector<uint64_t> tot(d, 0);
@@ -638,6 +647,8 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
     stats->top_levels = T, stats->n_roots = (int)nroots, stats->n_solutions = nrep, stats->n_devices = ndev;
     stats->n_rounds = rounds;
     stats->final_maxdist = cur, stats->device_ms = ms_max;
+    stats->host_breadth_us = (float)std::chrono::duration<double, std::micro>(t_host - t_begin).count();
+    stats->total_us = (float)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
   }
   if (overflow)
   {

@@ -1,0 +1,62 @@
+// fplll_extenum_adapter.cpp — the reference-side binding of the device enumerator.
+//
+// Compiled AGAINST fplll's own headers (it needs std::function typedefs from fplll/enum/enumerate_ext_api.h) and
+// linked into the application that links libfplll; everything below the typedef'd signature is the plain C-ABI of
+// include/b200enum.h.  Registration is one call: b200_enum_register(ngpus) -> fplll::set_external_enumerator(...)
+// (fplll/enum/enumerate_ext.h:100), or at configure time  --with-extenum-func=b200_enumerate  (configure.ac:187-210).
+//
+// Not part of libb200enum.so: /root/reference's headers do not exist on the GPU box, so this file is built only
+// where fplll is installed (tests/ builds it against oracle/_ref in the development container to prove it links and
+// runs — see INTEGRATION.md).
+#include <fplll/fplll.h>
+
+#include <array>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/b200enum.h"
+
+namespace {
+
+int g_ngpus = 1;
+
+double trampoline(void *ctx, double dist, const double *sol)
+{
+  auto *f = static_cast<std::function<fplll::extenum_cb_process_sol> *>(ctx);
+  return (*f)(dist, const_cast<double *>(sol));  // extenum_cb_process_sol returns the new bound (enumerate_ext_api.h:62)
+}
+
+}  // namespace
+
+// exactly fplll::extenum_fc_enumerate (enumerate_ext_api.h:88-92)
+std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM>
+b200_enumerate(const int dim, fplll::enumf maxdist, std::function<fplll::extenum_cb_set_config> cbfunc,
+               std::function<fplll::extenum_cb_process_sol> cbsol,
+               std::function<fplll::extenum_cb_process_subsol> /*cbsubsol*/, bool dual, bool findsubsols)
+{
+  std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM> ret{};
+  if (dual || findsubsols || dim < 2 || dim > B200ENUM_MAX_DIM)
+  {
+    ret[0] = ~uint64_t(0);  // "not supported": fplll uses its own enumerator (enumerate_ext.cpp:88), as enumlib does
+    return ret;
+  }
+  std::vector<double> mut((size_t)dim * dim, 0.0), rdiag(dim), pruning(dim);
+  cbfunc(mut.data(), dim, /*mutranspose=*/true, rdiag.data(), pruning.data());
+  std::vector<int> devs(g_ngpus);
+  for (int i = 0; i < g_ngpus; i++)
+    devs[i] = i;
+  std::vector<uint64_t> nodes(dim, 0);
+  const int rc = b200enum_run(dim, maxdist, mut.data(), rdiag.data(), pruning.data(), 0, devs.data(), g_ngpus, 0, 1,
+                              trampoline, &cbsol, nodes.data(), nullptr);
+  if (rc != B200ENUM_OK)  // a broken GPU must not silently turn into a CPU enumeration
+    throw std::runtime_error(std::string("b200_enumerate: ") + b200enum_last_error());
+  for (int i = 0; i < dim; i++)
+    ret[i] = nodes[i];
+  return ret;
+}
+
+extern "C" void b200_enum_register(int ngpus)
+{
+  g_ngpus = ngpus > 0 ? ngpus : 1;
+  fplll::set_external_enumerator(b200_enumerate);
+}

@@ -202,6 +202,8 @@ __global__ void k_set_r(Batch S, int i, int j, const double *f)
     v.r[tri_off(i) + j] = f[l];
     if (i == j)
       v.mu[mu_off(i, i)] = f[l];  // diagonal mirror (gso_layout.cuh)
+    v.meta[M_CLEAN_SR]  = min(v.meta[M_CLEAN_SR], i);
+    v.meta[M_CLEAN_LLL] = min(v.meta[M_CLEAN_LLL], i);
     if (v.valid[i] == j)
       v.valid[i] = j + 1;
   }
@@ -263,7 +265,8 @@ __global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row, int *va
 }
 
 template <int MAXQ>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_lll(Batch S, double delta, double eta, int *status, long *stats)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    k_lll(Batch S, double delta, double eta, int kmin, int kstart, int kend, int sr_start, int *status, long *stats)
 {
   View v;
   WarpSmem s;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_lll(Batch S, double delt
     return;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   LLLStats st;
-  const int r = warp_lll<MAXQ>(v, s, lov, delta, eta, lane, st);
+  const int r = warp_lll<MAXQ>(v, s, lov, delta, eta, kmin, kstart, kend, sr_start, lane, st);
   if (lane == 0)
   {
     status[l] = r;
@@ -282,6 +285,99 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_lll(Batch S, double delt
       stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
       stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
     }
+  }
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    k_size_reduction(Batch S, double eta, int kmin, int kend, int sr_start, int *status)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long iters  = 0;
+  const int r = warp_size_reduction<MAXQ>(v, s, kmin, kend, sr_start, eta, lane, iters);
+  if (lane == 0)
+    status[l] = r;
+}
+
+__global__ void k_apply_ops(Batch S, const b200gso_op *ops, int n)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  for (int t = 0; t < n; t++)
+  {
+    const b200gso_op op = ops[t];
+    switch (op.type)
+    {
+    case B200GSO_OP_ROW_ADDMUL: warp_row_addmul_we(v, op.a, op.b, op.x, 0, lane); break;
+    case B200GSO_OP_MOVE_ROW: warp_move_row(v, op.a, op.b, lane); break;
+    case B200GSO_OP_ROW_SWAP: warp_row_swap(v, op.a, op.b, lane); break;
+    case B200GSO_OP_ROW_OP_END: warp_row_op_end(v, op.a, op.b, lane); break;
+    case B200GSO_OP_NEGATE:
+      lower_clean(v, op.a, lane);
+      for (int c = lane; c < v.n; c += 32)
+        v.b[(size_t)op.a * v.ldb + c] = -v.b[(size_t)op.a * v.ldb + c];
+      break;
+    }
+    __syncwarp();
+  }
+}
+
+// MatGSO::negate_row_of_b(i), gso.h:291-297 (integer row only)
+__global__ void k_negate_row(Batch S, int i)
+{
+  const int l = blockIdx.y;
+  View v      = S.view(l);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    v.meta[M_CLEAN_SR]  = min(v.meta[M_CLEAN_SR], i);
+    v.meta[M_CLEAN_LLL] = min(v.meta[M_CLEAN_LLL], i);
+  }
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < S.n; c += gridDim.x * blockDim.x)
+    v.b[(size_t)i * S.ldb + c] = -v.b[(size_t)i * S.ldb + c];
+}
+
+__global__ void k_get_r_diag(Batch S, int l, int first, int count, double *rmant, long *rexpo)
+{
+  View v = S.view(l);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  {
+    rmant[i] = v.r[tri_off(first + i) + first + i];
+    rexpo[i] = v.row_expo_en ? 2L * v.row_expo[first + i] : 0L;
+  }
+}
+
+// What Enumeration::enumerate pulls out of the GSO for a block (enumerate.cpp:91-141, enumerate_ext.cpp:91-148):
+// mut[k*beta+j] = get_mu(first+j, first+k) for j > k (true value, row_expo applied), and r(first+i,first+i) as
+// (mantissa, exponent) = get_r_exp.  Lattice l only.
+__global__ void k_get_block(Batch S, int l, int first, int beta, double *mut, double *rmant, long *rexpo)
+{
+  View v = S.view(l);
+  for (int t = threadIdx.x; t < beta * beta; t += blockDim.x)
+  {
+    const int k = t / beta, j = t % beta;
+    double val = 0.0;
+    if (j > k)
+    {
+      val = v.mu[mu_off(first + j, first + k)];
+      if (v.row_expo_en)
+        val = ldexp(val, v.row_expo[first + j] - v.row_expo[first + k]);
+    }
+    mut[t] = val;
+  }
+  for (int i = threadIdx.x; i < beta; i += blockDim.x)
+  {
+    rmant[i] = v.r[tri_off(first + i) + first + i];
+    rexpo[i] = v.row_expo_en ? 2L * v.row_expo[first + i] : 0L;
   }
 }
 
@@ -422,7 +518,9 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row<8>, (const void *)k_update_row<6>, (const void *)k_update_row<5>,
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
-                       (const void *)k_lll<4>,       (const void *)k_lll<8>,       (const void *)k_lll<16>};
+                       (const void *)k_lll<4>,       (const void *)k_lll<8>,       (const void *)k_lll<16>,
+                       (const void *)k_size_reduction<4>, (const void *)k_size_reduction<8>,
+                       (const void *)k_size_reduction<16>, (const void *)k_apply_ops};
   for (const void *f : fns)
     CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
@@ -698,33 +796,139 @@ int b200gso_get_mu_r_row(b200gso_t *h, int i, double *mu_row, double *r_row, int
   return 0;
 }
 
-int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats)
+static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int kmin, int kstart, int kend, int sr_start,
+                        int *status, long *stats)
 {
   if (!h || !status)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
   const Batch &S = h->S;
-  if (S.d > 512)
+  if (kend < 0)
+    kend = S.d;
+  if (S.d > 512 || kmin < 0 || kstart < kmin || kend > S.d || kstart >= kend + (mode ? 1 : 0) || sr_start < 0)
   {
-    g_err = "b200gso_lll: d > 512 not supported by the warp-resident Babai registers";
+    g_err = "b200gso_lll/size_reduction: bad range (or d > 512)";
     return B200GSO_EINVAL;
   }
-  int *d_st = nullptr;
+  int *d_st     = h->d_ok;
   long *d_stats = nullptr;
-  CK(cudaMallocAsync(&d_st, sizeof(int) * S.B, h->stream));
-  CK(cudaMallocAsync(&d_stats, sizeof(long) * 4 * S.B, h->stream));
+  if (stats)
+    CK(cudaMallocAsync(&d_stats, sizeof(long) * 4 * S.B, h->stream));
   const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
+#define LLL_LAUNCH(Q)                                                                                          \
+  do                                                                                                           \
+  {                                                                                                            \
+    if (mode == 0)                                                                                             \
+      k_lll<Q><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats); \
+    else                                                                                                       \
+      k_size_reduction<Q><<<g, t, h->smem_bytes, h->stream>>>(S, eta, kmin, kend, sr_start, d_st);             \
+  } while (0)
   if (S.d <= 128)
-    k_lll<4><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+    LLL_LAUNCH(4);
   else if (S.d <= 256)
-    k_lll<8><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+    LLL_LAUNCH(8);
   else
-    k_lll<16><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, d_st, d_stats);
+    LLL_LAUNCH(16);
+#undef LLL_LAUNCH
   CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
   if (stats)
+  {
     CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaFreeAsync(d_st, h->stream));
-  CK(cudaFreeAsync(d_stats, h->stream));
+    CK(cudaFreeAsync(d_stats, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats)
+{
+  return lll_dispatch(h, 0, delta, eta, 0, 0, -1, 0, status, stats);
+}
+
+int b200gso_lll_range(b200gso_t *h, double delta, double eta, int kappa_min, int kappa_start, int kappa_end,
+                      int size_reduction_start, int *status, long *stats)
+{
+  return lll_dispatch(h, 0, delta, eta, kappa_min, kappa_start, kappa_end, size_reduction_start, status, stats);
+}
+
+int b200gso_size_reduction(b200gso_t *h, double eta, int kappa_min, int kappa_end, int size_reduction_start,
+                           int *status)
+{
+  return lll_dispatch(h, 1, 0.99, eta, kappa_min, kappa_min, kappa_end, size_reduction_start, status, nullptr);
+}
+
+int b200gso_negate_row_of_b(b200gso_t *h, int i)
+{
+  if (!h || i < 0 || i >= h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  dim3 g(1, h->S.B);
+  k_negate_row<<<g, 256, 0, h->stream>>>(h->S, i);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_apply_ops(b200gso_t *h, const b200gso_op *ops, int n)
+{
+  if (!h || (n > 0 && !ops) || n < 0)
+    return B200GSO_EINVAL;
+  if (n == 0)
+    return 0;
+  for (int t = 0; t < n; t++)
+  {
+    const b200gso_op &o = ops[t];
+    const bool two = o.type == B200GSO_OP_ROW_ADDMUL || o.type == B200GSO_OP_MOVE_ROW || o.type == B200GSO_OP_ROW_SWAP;
+    if (o.type < 1 || o.type > 5 || o.a < 0 || o.a >= h->S.d || (two && (o.b < 0 || o.b >= h->S.d)) ||
+        (o.type == B200GSO_OP_ROW_OP_END && (o.b < o.a || o.b > h->S.d)))
+    {
+      g_err = "b200gso_apply_ops: bad op";
+      return B200GSO_EINVAL;
+    }
+  }
+  CK(cudaSetDevice(h->device));
+  b200gso_op *d_ops = nullptr;
+  CK(cudaMallocAsync(&d_ops, sizeof(b200gso_op) * n, h->stream));
+  CK(cudaMemcpyAsync(d_ops, ops, sizeof(b200gso_op) * n, cudaMemcpyHostToDevice, h->stream));
+  k_apply_ops<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, d_ops, n);
+  CK(cudaFreeAsync(d_ops, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // `ops` is caller memory
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_get_r_diag(b200gso_t *h, int lattice, int first, int count, double *r_mant, long *r_expo)
+{
+  if (!h || lattice < 0 || lattice >= h->S.B || first < 0 || count < 1 || first + count > h->S.d || !r_mant || !r_expo)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  double *t = nullptr;
+  CK(cudaMallocAsync(&t, (size_t)count * (8 + sizeof(long)), h->stream));
+  long *te = (long *)(t + count);
+  k_get_r_diag<<<(count + 127) / 128, 128, 0, h->stream>>>(h->S, lattice, first, count, t, te);
+  CK(cudaMemcpyAsync(r_mant, t, (size_t)count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(r_expo, te, (size_t)count * sizeof(long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaFreeAsync(t, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_get_block(b200gso_t *h, int lattice, int first, int beta, double *mut, double *r_mant, long *r_expo)
+{
+  if (!h || lattice < 0 || lattice >= h->S.B || first < 0 || beta < 1 || first + beta > h->S.d || !mut || !r_mant ||
+      !r_expo)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  double *t = nullptr;
+  const size_t nd = (size_t)beta * beta + beta;
+  CK(cudaMallocAsync(&t, nd * 8 + beta * sizeof(long), h->stream));
+  long *te = (long *)(t + nd);
+  k_get_block<<<1, 256, 0, h->stream>>>(h->S, lattice, first, beta, t, t + (size_t)beta * beta, te);
+  CK(cudaMemcpyAsync(mut, t, (size_t)beta * beta * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(r_mant, t + (size_t)beta * beta, beta * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(r_expo, te, beta * sizeof(long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaFreeAsync(t, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;

@@ -44,7 +44,14 @@ __host__ __device__ inline size_t bf_size(int d, int n) { return (size_t)n_panel
 __host__ __device__ inline int ld_b(int n) { return (n + 1) & ~1; }
 
 // meta[] slots (per lattice)
-enum { M_NKR = 0, M_NKC = 1, M_NSR = 2, M_LOCKED = 3, M_STRIDE = 8 };
+// M_CLEAN_SR / M_CLEAN_LLL: number of leading rows known to be size-reduced (eta) / LLL-reduced (delta, eta) with a
+// valid GSO — maintained so that a repeated lll(0,0,k) / size_reduction(0,k) call resumes at the first row that was
+// touched since, instead of re-walking rows on which the reference's loop is a proven no-op (gso_lll.cuh).
+enum
+{
+  M_NKR = 0, M_NKC = 1, M_NSR = 2, M_LOCKED = 3, M_CLEAN_SR = 4, M_CLEAN_LLL = 5,
+  M_DELTA_LO = 6, M_DELTA_HI = 7, M_ETA_LO = 8, M_ETA_HI = 9, M_STRIDE = 16
+};
 
 // One lattice's state (device pointers).
 struct View

@@ -211,22 +211,83 @@ __device__ inline double warp_get_gram_diag(const View &v, WarpSmem &s, int i, i
   return val;
 }
 
-// LLLReduction::lll(kappa_min=0, kappa_start=0, kappa_end=d), lll.cpp:44-164; LLL_DEFAULT flags (no siegel, no
-// early reduction, not verbose).  lov = shared array of d+1 doubles.
+// LLLReduction::size_reduction(kappa_min, kappa_end, size_reduction_start), lll.h:106-122
 template <int MAXQ>
-__device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double delta, double eta, int lane,
-                               LLLStats &st)
+__device__ inline int warp_size_reduction(const View &v, WarpSmem &s, int kappa_min, int kappa_end, int sr_start,
+                                          double eta, int lane, long &iters)
 {
-  const int d = v.d, kappa_end = d;
-  int kappa = 1, zeros = 0;
+  // Rows below the clean prefix are size-reduced with a valid GSO and untouched since: on them the reference's loop
+  // body (babai finds nothing to reduce, update_gso_row finds the row valid) changes no state, so start after them.
+  const bool eta_same = (v.meta[M_ETA_LO] == __double2loint(eta)) && (v.meta[M_ETA_HI] == __double2hiint(eta));
+  const int clean     = (eta_same && sr_start == 0) ? v.meta[M_CLEAN_SR] : 0;
+  const int k_first   = (kappa_min <= clean) ? max(kappa_min, min(clean, kappa_end)) : kappa_min;
+  __syncwarp();
+  for (int k = k_first; k < kappa_end; k++)
+  {
+    if (k > 0)
+    {
+      const int st = warp_babai<MAXQ>(v, s, k, k, sr_start, eta, lane, iters);
+      if (st != RED_SUCCESS)
+        return st;
+    }
+    if (!warp_update_gso_row(v, k, k, s, lane))
+      return RED_GSO_FAILURE;  // the reference returns false here without touching status (lll.h:118-119)
+  }
+  if (sr_start == 0 && kappa_min <= clean && lane == 0)
+  {
+    // rows [0, k_first) were clean, rows [k_first, kappa_end) have just been size-reduced (row operations inside
+    // this loop only lowered the marker to rows >= k_first, which were then redone)
+    if (!eta_same)
+    {
+      v.meta[M_ETA_LO]    = __double2loint(eta);
+      v.meta[M_ETA_HI]    = __double2hiint(eta);
+      v.meta[M_CLEAN_LLL] = 0;
+      v.meta[M_CLEAN_SR]  = kappa_end;
+    }
+    else
+      v.meta[M_CLEAN_SR] = max(v.meta[M_CLEAN_SR], kappa_end);
+  }
+  __syncwarp();
+  return RED_SUCCESS;
+}
+
+// LLLReduction::lll(kappa_min, kappa_start, kappa_end, size_reduction_start), lll.cpp:44-164; LLL_DEFAULT flags
+// (no siegel, no early reduction, not verbose).  lov = shared array of d+1 doubles.
+template <int MAXQ>
+__device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double delta, double eta, int kappa_min,
+                               int kappa_start, int kappa_end, int sr_start, int lane, LLLStats &st)
+{
+  const int d = kappa_end - kappa_min;
+  int kappa = kappa_start + 1, zeros = 0;
   st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
   const double swap_threshold = delta;
+  // Clean prefix: rows [0, c) are (delta, eta)-LLL-reduced with a valid GSO and untouched since the call that made
+  // them so.  On such rows every iteration of the reference's loop is a no-op on the state (babai finds |mu| <= eta,
+  // Lovasz holds, set_r re-writes the value the same chain produced before), so the loop may start at row c.
+  const bool par_same = v.meta[M_ETA_LO] == __double2loint(eta) && v.meta[M_ETA_HI] == __double2hiint(eta) &&
+                        v.meta[M_DELTA_LO] == __double2loint(delta) && v.meta[M_DELTA_HI] == __double2hiint(delta);
+  const bool track    = (kappa_min == 0 && kappa_start == 0 && sr_start == 0);
+  if (track && par_same)
+    kappa = max(kappa, min(v.meta[M_CLEAN_LLL], kappa_end));
+  __syncwarp();
   for (; zeros < d && warp_b_row_is_zero(v, 0, lane); zeros++)
-    warp_move_row(v, 0, kappa_end - 1 - zeros, lane);
-  if (zeros < d && !warp_update_gso_row(v, 0, 0, s, lane))
+    warp_move_row(v, kappa_min, kappa_end - 1 - zeros, lane);
+  if (zeros < d)
   {
-    st.zeros = zeros;
-    return RED_GSO_FAILURE;
+    if (kappa_start > 0)
+    {
+      const int bst = warp_babai<MAXQ>(v, s, kappa_start, kappa_start, sr_start, eta, lane, st.babai_iters);
+      if (bst != RED_SUCCESS)
+      {
+        st.final_kappa = kappa_start, st.zeros = zeros;
+        return bst;
+      }
+    }
+    if (!warp_update_gso_row(v, kappa_start, kappa_start, s, lane))
+    {
+      st.final_kappa = kappa_start, st.zeros = zeros;
+      return RED_GSO_FAILURE;
+    }
   }
   const long maxe = warp_max_exp_of_b(v, lane);
   const long long max_iter =
@@ -234,7 +295,7 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
   long long iter;
   for (iter = 0; iter < max_iter && kappa < kappa_end - zeros; iter++)
   {
-    const int bst = warp_babai<MAXQ>(v, s, kappa, kappa, 0, eta, lane, st.babai_iters);
+    const int bst = warp_babai<MAXQ>(v, s, kappa, kappa, sr_start, eta, lane, st.babai_iters);
     if (bst != RED_SUCCESS)
     {
       st.final_kappa = kappa, st.zeros = zeros;
@@ -257,7 +318,7 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
       if (thr > lov[kappa - 1])
       {
         int kk = kappa;
-        for (kk--; kk > 0; kk--)
+        for (kk--; kk > kappa_min; kk--)
         {
           double t2 = __dmul_rn(v.r[tri_off(kk - 1) + kk - 1], swap_threshold);
           if (v.row_expo_en)
@@ -293,7 +354,26 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     kappa++;
   }
   st.zeros = zeros;
-  return (kappa < kappa_end - zeros) ? RED_LLL_FAILURE : RED_SUCCESS;
+  if (kappa < kappa_end - zeros)
+    return RED_LLL_FAILURE;
+  if (track && lane == 0)
+  {
+    const int upto = kappa_end - zeros;
+    if (!par_same)
+    {
+      v.meta[M_ETA_LO] = __double2loint(eta), v.meta[M_ETA_HI] = __double2hiint(eta);
+      v.meta[M_DELTA_LO] = __double2loint(delta), v.meta[M_DELTA_HI] = __double2hiint(delta);
+      v.meta[M_CLEAN_LLL] = upto;
+      v.meta[M_CLEAN_SR]  = upto;
+    }
+    else
+    {
+      v.meta[M_CLEAN_LLL] = max(v.meta[M_CLEAN_LLL], upto);
+      v.meta[M_CLEAN_SR]  = max(v.meta[M_CLEAN_SR], upto);
+    }
+  }
+  __syncwarp();
+  return RED_SUCCESS;
 }
 
 }  // namespace b200

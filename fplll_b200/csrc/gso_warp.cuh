@@ -32,6 +32,16 @@ struct WarpSmem
   }
 };
 
+// Row `idx` (and possibly everything after it) has been modified: the "already reduced" prefix ends there.
+__device__ inline void lower_clean(const View &v, int idx, int lane)
+{
+  if (lane == 0)
+  {
+    v.meta[M_CLEAN_SR]  = min(v.meta[M_CLEAN_SR], idx);
+    v.meta[M_CLEAN_LLL] = min(v.meta[M_CLEAN_LLL], idx);
+  }
+}
+
 // FP_NR<double>::exponent, nr_FP_d.inl:44
 __device__ inline long fexponent(double x) { return (long)ilogb(x) + 1; }
 
@@ -338,6 +348,7 @@ __device__ inline void warp_row_op_end(const View &v, int first, int last, int l
   }
   for (int i = last + lane; i < nkr; i += 32)
     v.valid[i] = min(v.valid[i], first);
+  lower_clean(v, first, lane);
   __syncwarp();
 }
 
@@ -349,6 +360,7 @@ __device__ inline void warp_row_addmul_we(const View &v, int i, int j, double x,
   const long lx = get_si_exp_we(x, expo, expo_add);
   if (expo == 0 && lx == 0)
     return;
+  lower_clean(v, i, lane);
   const int nc           = v.meta[M_NKC];
   unsigned long long *bi = (unsigned long long *)(v.b + (size_t)i * v.ldb);
   const unsigned long long *bj = (const unsigned long long *)(v.b + (size_t)j * v.ldb);
@@ -369,6 +381,7 @@ __device__ inline void warp_row_addmul_we(const View &v, int i, int j, double x,
 __device__ inline void warp_row_swap(const View &v, int i, int j, int lane)
 {
   int64_t *a = v.b + (size_t)i * v.ldb, *b = v.b + (size_t)j * v.ldb;
+  lower_clean(v, min(i, j), lane);
   for (int c = lane; c < v.n; c += 32)
   {
     int64_t t = a[c];
@@ -402,6 +415,7 @@ __device__ inline void warp_move_row(const View &v, int old_r, int new_r, int la
   const int lo = right ? new_r : old_r, hi = right ? old_r : new_r;
   for (int i = lo + lane; i < nkr; i += 32)
     v.valid[i] = min(v.valid[i], lo);
+  lower_clean(v, lo, lane);
   __syncwarp();
   // mu (columns k < lo) — panel layout
   for (int k = lane; k < lo; k += 32)
@@ -468,26 +482,41 @@ __device__ inline void warp_move_row(const View &v, int old_r, int new_r, int la
     }
   }
   // gf: new(i,j) = old_sym(s(i), s(j)) on the known rows; rotate_gram_left only when old_r < nkr-1 and up to
-  // min(new_r, nkr-1) (gso.cpp:338-341)
+  // min(new_r, nkr-1) (gso.cpp:338-341).  Rows below the rotated range only permute their columns [lo, ghi] (done in
+  // place, one row per lane); the rotated rows themselves are rebuilt from a scratch copy of just those rows.
   {
     const int ghi = right ? hi : min(hi, nkr - 1);
     if (right || lo < nkr - 1)
     {
-      const size_t beg = tri_off(lo), end = tri_off(nkr);
+      for (int i = ghi + 1 + lane; i < nkr; i += 32)
+      {
+        double *row = v.gf + tri_off(i);
+        if (right)
+        {
+          const double t = row[ghi];
+          for (int j = ghi; j > lo; --j)
+            row[j] = row[j - 1];
+          row[lo] = t;
+        }
+        else
+        {
+          const double t = row[lo];
+          for (int j = lo; j < ghi; ++j)
+            row[j] = row[j + 1];
+          row[ghi] = t;
+        }
+      }
+      const size_t beg = tri_off(lo), end = tri_off(ghi + 1);
       for (size_t t = beg + lane; t < end; t += 32)
         v.scratch[t - beg] = v.gf[t];
       __syncwarp();
-      for (int i = lo; i < nkr; i++)
+      for (int i = lo; i <= ghi; i++)
       {
-        int si = i;
-        if (i >= lo && i <= ghi)
-          si = right ? (i == lo ? ghi : i - 1) : (i == ghi ? lo : i + 1);
-        // columns touched: all j<=i if row i is rotated, else only j in [lo, ghi]
-        const int jb = (i <= ghi) ? 0 : lo, je = (i <= ghi) ? i : ghi;
-        for (int j = jb + lane; j <= je; j += 32)
+        const int si = right ? (i == lo ? ghi : i - 1) : (i == ghi ? lo : i + 1);
+        for (int j = lane; j <= i; j += 32)
         {
           int sj = j;
-          if (j >= lo && j <= ghi)
+          if (j >= lo)
             sj = right ? (j == lo ? ghi : j - 1) : (j == ghi ? lo : j + 1);
           const int a = max(si, sj), b = min(si, sj);
           v.gf[tri_off(i) + j] = v.scratch[tri_off(a) + b - beg];

@@ -16,7 +16,8 @@ _CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, _P(C.c_double))
 class _Stats(C.Structure):
     _fields_ = [("host_nodes", C.c_uint64), ("device_nodes", C.c_uint64), ("leaves", C.c_uint64),
                 ("top_levels", C.c_int), ("n_roots", C.c_int), ("n_solutions", C.c_int), ("n_devices", C.c_int), ("n_rounds", C.c_int),
-                ("final_maxdist", C.c_double), ("device_ms", C.c_float)]
+                ("final_maxdist", C.c_double), ("device_ms", C.c_float), ("host_breadth_us", C.c_float),
+                ("total_us", C.c_float)]
 
 
 _done = False

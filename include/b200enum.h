@@ -50,6 +50,8 @@ typedef struct
   int n_rounds;          /* kernel rounds (budgeted walk + work split) */
   double final_maxdist;
   float device_ms; /* max over devices of the kernel time (CUDA events on the launching streams) */
+  float host_breadth_us; /* wall time of the host breadth phase */
+  float total_us;        /* wall time of the whole call */
 } b200enum_stats;
 
 /* Enumerate { x in Z^dim, x != 0 :  sum_k rdiag[k] * (x_k + sum_{j>k} mut[k*dim+j] * x_j)^2  <=  pruning[k]-bounded

@@ -100,6 +100,36 @@ int b200gso_get_mu_r_row(b200gso_t *h, int i, double *mu_row, double *r_row, int
  * stats (may be NULL): batch*4 = {n_swaps, final_kappa, zeros, babai_iterations}. */
 int b200gso_lll(b200gso_t *h, double delta, double eta, int *status, long *stats);
 
+/* LLLReduction::lll(kappa_min, kappa_start, kappa_end, size_reduction_start), lll.cpp:44-164 (kappa_end = -1: d). */
+int b200gso_lll_range(b200gso_t *h, double delta, double eta, int kappa_min, int kappa_start, int kappa_end,
+                      int size_reduction_start, int *status, long *stats);
+/* LLLReduction::size_reduction(kappa_min, kappa_end, size_reduction_start), lll.h:106-122.  status[l] = RedStatus. */
+int b200gso_size_reduction(b200gso_t *h, double eta, int kappa_min, int kappa_end, int size_reduction_start,
+                           int *status);
+/* MatGSO::negate_row_of_b(i), gso.h:291-297 (bracket with row_op_begin/end like the reference's callers). */
+int b200gso_negate_row_of_b(b200gso_t *h, int i);
+/* What Enumeration pulls out of the GSO for block [first, first+beta) of lattice `lattice` (enumerate.cpp:91-141,
+ * enumerate_ext.cpp:91-148): mut[k*beta+j] = get_mu(first+j, first+k) for j > k (true value, row exponents applied)
+ * and get_r_exp(first+i, first+i) as mantissa r_mant[i] and exponent r_expo[i]. */
+int b200gso_get_block(b200gso_t *h, int lattice, int first, int beta, double *mut, double *r_mant, long *r_expo);
+
+/* A recorded sequence of the calls above, executed in order by ONE kernel launch on every lattice of the batch —
+ * what BKZ's svp_postprocessing / rerandomize_block issue as dozens of individual calls (bkz.cpp:43-80,128-272). */
+typedef struct
+{
+  int type, a, b, pad; /* ROW_ADDMUL: row_addmul(a, b, x); MOVE_ROW: move_row(a, b); ROW_SWAP: row_swap(a, b); */
+  double x;            /* ROW_OP_END: row_op_end(a, b); NEGATE: negate_row_of_b(a) */
+} b200gso_op;
+#define B200GSO_OP_ROW_ADDMUL 1
+#define B200GSO_OP_MOVE_ROW 2
+#define B200GSO_OP_ROW_SWAP 3
+#define B200GSO_OP_ROW_OP_END 4
+#define B200GSO_OP_NEGATE 5
+int b200gso_apply_ops(b200gso_t *h, const b200gso_op *ops, int n);
+
+/* get_r_exp(first+i, first+i) for i < count of lattice `lattice` (gso_interface.h:704-722): mantissa and exponent. */
+int b200gso_get_r_diag(b200gso_t *h, int lattice, int first, int count, double *r_mant, long *r_expo);
+
 /* Timing helper for bench.py: runs `reps` back-to-back steps { row_op_end(i,i+1); update_gso_row(i,i) }
  * (invalidate != 0) or { invalidate_gso_row(i,0); update_gso_row(i,i) } on the handle's stream, timed with CUDA
  * events ON THAT STREAM: *ms_update_mean = mean device time of ONE update_gso_row launch (events around each

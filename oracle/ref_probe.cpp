@@ -308,7 +308,7 @@ int main(int argc, char **argv)
       puts("load P | save P | tolong | gso l|m FLAGS | update_gso | update_row I J | discover_all | "
            "row_addmul_we I J X E | row_op_begin F L | row_op_end F L | move_row O N | row_swap I J | "
            "set_r I J V | dump P | dumpb P | lll DELTA ETA METHOD FLOAT FLAGS | islll DELTA ETA | "
-           "enum FIRST LAST FACTOR PRUNEFILE OUT internal|enumlib|capture | set_threads T | time_update_row I REPS INV | time_update_row_mt I REPS T PER | time_update_gso_mt REPS T PER");
+           "bkz BLOCK FLAGS MAXLOOPS default|none internal|enumlib THREADS | enum FIRST LAST FACTOR PRUNEFILE OUT internal|enumlib|capture | set_threads T | time_update_row I REPS INV | time_update_row_mt I REPS T PER | time_update_gso_mt REPS T PER");
     }
     else if (c == "load")
     {
@@ -513,6 +513,35 @@ int main(int argc, char **argv)
       int t;
       is >> t;
       printf("set_threads %d\n", set_threads(t));
+    }
+    else if (c == "bkz")
+    {
+      /* bkz BLOCK FLAGS MAXLOOPS STRATEGIES(default|none) ENUM(internal|enumlib) THREADS : bkz_reduction(&Bm, NULL, param,
+         FT_DOUBLE) — bkz.cpp:849-927 — on the mpz matrix (converted to long inside when entries fit, bkz.cpp:826) */
+      int bs, fl, ml, th;
+      string strat, em;
+      is >> bs >> fl >> ml >> strat >> em >> th;
+      static std::function<extenum_fc_enumerate> bundled = get_external_enumerator();
+      set_external_enumerator(em == "internal" ? std::function<extenum_fc_enumerate>(nullptr) : bundled);
+      set_threads(th);
+      vector<Strategy> strategies;
+      if (strat == "default")
+        strategies = load_strategies_json(strategy_full_path("default.json"));
+      BKZParam param(bs, strategies);
+      param.flags     = fl;
+      param.max_loops = ml;
+      double t0       = now();
+      int st          = -100;
+      try
+      {
+        st = bkz_reduction(&Bm, NULL, param, FT_DOUBLE, 0);
+      }
+      catch (std::exception &e)
+      {
+        printf("bkz exception %s\n", e.what());
+      }
+      set_external_enumerator(bundled);
+      printf("bkz status=%d sec=%.6f\n", st, now() - t0);
     }
     else if (c == "time_update_row")
     {

@@ -31,7 +31,27 @@ def gen(args, name):
     return p
 
 
+def bkz_fixtures():
+    # --- BKZ fixtures: q-ary dim-60 (latticegen q 60 30 12 b), reference wrapper-LLL, then reference BKZ ----------
+    q60 = gen(["q", 60, 30, 12, "b"], "q60.txt")
+    q60l = os.path.join(TMP, "q60_lll.txt")
+    O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (q60, q60l))
+    b_in = np.array(O.read_matrix(q60l), dtype=np.int64)
+    pack = {"b_in": b_in}
+    # (block, flags, max_loops, strategies): BKZ_NO_LLL = 2, BKZ_MAX_LOOPS = 4
+    for tag, bs, fl, ml, strat in [("bkz20_none", 20, 2, 0, "none"), ("bkz30_default", 30, 2 | 4, 2, "default"),
+                                   ("bkz40_default", 40, 2 | 4, 2, "default")]:
+        outp = os.path.join(TMP, "q60_%s.txt" % tag)
+        o = O.run_ref("load %s\nbkz %d %d %d %s enumlib 1\nsave %s\n" % (q60l, bs, fl, ml, strat, outp), timeout=600)
+        st = int(o.split("bkz status=")[1].split()[0])
+        pack[tag + "_status"] = np.int32(st)
+        pack[tag + "_b"] = np.array(O.read_matrix(outp), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "bkz_q60.npz"), **pack)
+
+
 def main():
+    if '--only-bkz' in sys.argv:
+        return bkz_fixtures()
     # --- config #1 input: latticegen u 40 40 (md5 a6fe01e1...) -------------------------------
     u40 = np.array(O.read_matrix(gen(["u", 40, 40], "u40.txt")), dtype=np.int64)
     s = O.RefSession(u40)
@@ -126,6 +146,7 @@ def main():
     lo = os.path.join(TMP, "leech_lll.txt")
     O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (leech_in, lo))
     np.savez_compressed(os.path.join(HERE, "leech_lll.npz"), b=np.array(O.read_matrix(lo), dtype=np.int64))
+    bkz_fixtures()
     print("golden fixtures written to", HERE)
 
 

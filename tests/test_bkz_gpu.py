@@ -1,0 +1,65 @@
+"""GPU tests of the BKZ driver (include/b200bkz.h: host control flow over device GSO/LLL + device enumeration)
+against runs of the reference's own bkz_reduction (tests/golden/bkz_q60.npz, made by make_golden.py)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fplll_b200
+    return fplll_b200
+
+
+def gso_profile(b):
+    m = O.OracleGSO(b, 0)
+    assert m.update_gso()
+    s = m.state()
+    return np.array([s["r"][i, i] for i in range(b.shape[0])])
+
+
+def test_bkz20_without_pruning_walks_the_reference_trajectory(fb):
+    """No pruning => no rerandomisation => BKZ is deterministic: device LLL (bit-identical to the reference's) +
+    device enumeration (same best vector) must end on the SAME basis as the reference's bkz_reduction."""
+    z = H.gold("bkz_q60.npz")
+    b = z["b_in"].copy()
+    st, stats = fb.bkz_reduction(b, fb.BKZParam(20, strategies=None, flags=fb.BKZ_NO_LLL))
+    assert st == int(z["bkz20_none_status"]) == 0
+    assert np.array_equal(b, z["bkz20_none_b"])
+    assert stats["enum_calls"] > 0 and stats["enum_nodes"] > 0
+
+
+@pytest.mark.parametrize("tag,bs", [("bkz30_default", 30), ("bkz40_default", 40)])
+def test_bkz_default_strategies_same_status_and_quality(fb, tag, bs):
+    """strategies/default.json (pruning + preprocessing + rerandomisation): the RNG differs from the reference's GMP
+    state, so compare what the reference's tests compare (status, tests/test_bkz.cpp:42-56) plus reduction quality."""
+    z = H.gold("bkz_q60.npz")
+    b = z["b_in"].copy()
+    st, stats = fb.bkz_reduction(b, fb.BKZParam(bs, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
+                                                max_loops=2))
+    assert st == int(z[tag + "_status"]) == 8  # RED_BKZ_LOOPS_LIMIT
+    ref, got, inp = gso_profile(z[tag + "_b"]), gso_profile(b), gso_profile(z["b_in"])
+    # same lattice: determinant preserved exactly (unimodular row operations on an int64 basis)
+    assert abs(np.sum(np.log(got)) - np.sum(np.log(inp))) < 1e-6
+    # first vector at least as good as LLL's and within 15% (squared) of the reference's BKZ output
+    assert got[0] <= inp[0] and got[0] <= 1.15 * ref[0]
+    # slope of log r_ii within 10% of the reference's
+    ix = np.arange(len(got))
+    s_ref, s_got = np.polyfit(ix, np.log(ref), 1)[0], np.polyfit(ix, np.log(got), 1)[0]
+    assert abs(s_got - s_ref) < 0.1 * abs(s_ref)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not shipped")
+def test_bkz_output_is_lll_reduced_by_the_reference_checker(fb, tmp_path):
+    z = H.gold("bkz_q60.npz")
+    b = z["b_in"].copy()
+    st, _ = fb.bkz_reduction(b, fb.BKZParam(30, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
+                                            max_loops=1))
+    assert st == 8
+    p = tmp_path / "out.txt"
+    O.write_matrix(str(p), b)
+    assert "islll 1" in O.run_ref("load %s\nislll 0.99 0.51\n" % p)

@@ -88,3 +88,21 @@ def test_dual_and_subsols_are_declined_like_enumlib(en):
         with pytest.raises(fb.B200Error) as e:
             en.enumerate_svp(z["mut"], z["rdiag"], None, float(z["maxdist"]), flags=fl)
         assert "(-5)" in str(e.value)
+
+
+def test_reference_bkz_with_the_plugin_installed(tmp_path):
+    """INTEGRATION.md end to end: the UNMODIFIED reference library runs its own bkz_reduction with the device
+    enumerator installed through set_external_enumerator (tests/plugin_demo.cpp + fplll_extenum_adapter.cpp).
+    BKZ-20 without pruning is deterministic, so the output must equal the reference's own (enumlib) output."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "plugin_demo")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/plugin_demo not built (needs the reference headers)")
+    z = H.gold("bkz_q60.npz")
+    inp, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    O.write_matrix(inp, z["b_in"])
+    p = subprocess.run([exe, inp, out, "20", "2", "0", "none", "b200"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "status=0" in p.stdout
+    assert np.array_equal(np.array(O.read_matrix(out), dtype=np.int64), z["bkz20_none_b"])
