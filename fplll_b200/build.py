@@ -14,6 +14,7 @@ TARGETS = {
     "libb200gso.so": ["gso_api.cu"],
     "libb200enum.so": ["enum_api.cu"],
     "libb200bkz.so": ["gso_api.cu", "enum_api.cu", "bkz_api.cu"],
+    "libb200hh.so": ["hh_api.cu"],
 }
 
 

@@ -6,7 +6,7 @@
 // (fplll/enum/enumerate_ext.h:100), or at configure time  --with-extenum-func=b200_enumerate  (configure.ac:187-210).
 //
 // Not part of libb200enum.so: /root/reference's headers do not exist on the GPU box, so this file is built only
-// where fplll is installed (tests/ builds it against oracle/_ref in the development container to prove it links and
+// where fplll is installed (tests/ builds it against the reference build of the development container to prove it links and
 // runs — see INTEGRATION.md).
 #include <fplll/fplll.h>
 

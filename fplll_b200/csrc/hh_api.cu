@@ -1,0 +1,754 @@
+// hh_api.cu — B200-native MatHouseholder<long,double> (HLLL data plane) behind include/b200hh.h.
+//
+// One warp per lattice (batches are the replica axis).  HBM layout per lattice: b (int64), bf, R, V
+// row-major d x n — update_R streams V_j[j..n) row by row (contiguous, 256-byte coalesced warp loads) against R_i held
+// in shared memory; the reference's R_history trace (householder.h:103-109) is kept in full when requested, addressed
+// through a per-row slot table so that swap() is the O(1) pointer swap it is in the reference.
+// Bit parity: a dot product is formed as element products in parallel (each correctly rounded, as the reference's
+// mul) followed by ONE lane adding them in ascending index order — the reference's exact chain (numvect.h:385-395).
+// In a batch the serial chain of one warp hides behind the other resident warps' HBM streaming (update_R moves
+// 16*T(i) bytes per lattice, 1.3 MB at i = 399, n = 400: ~0.5 ms of HBM time per warp, the chain is ~0.4 ms).
+#include "../../include/b200hh.h"
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int HW = 4;  // warps per CTA
+thread_local std::string g_err;
+#define CKH(call)                                                                                  \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+    {                                                                                              \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+      return B200HH_ECUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+enum { HM_NKR = 0, HM_NKC = 1, HM_UPDATED = 2, HM_STRIDE = 4 };
+
+struct HBatch
+{
+  int B, d, n, ldb, row_expo_en, keep_hist;
+  int64_t *b;
+  double *bf, *R, *V, *sigma, *nsb, *hist;
+  int *row_expo, *irs, *meta, *hslot;
+  long *ensb;
+};
+
+struct HView
+{
+  int d, n, ldb, row_expo_en, keep_hist;
+  int64_t *b;
+  double *bf, *R, *V, *sigma, *nsb, *hist;
+  int *row_expo, *irs, *meta, *hslot;
+  long *ensb;
+};
+
+__device__ inline HView hview(const HBatch &S, int l)
+{
+  HView v;
+  v.d = S.d, v.n = S.n, v.ldb = S.ldb, v.row_expo_en = S.row_expo_en, v.keep_hist = S.keep_hist;
+  const size_t dn = (size_t)S.d * S.n;
+  v.b        = S.b + (size_t)l * S.d * S.ldb;
+  v.bf       = S.bf + l * dn;
+  v.R        = S.R + l * dn;
+  v.V        = S.V + l * dn;
+  v.sigma    = S.sigma + (size_t)l * S.d;
+  v.nsb      = S.nsb + (size_t)l * S.d;
+  v.ensb     = S.ensb + (size_t)l * S.d;
+  v.hist     = S.keep_hist ? S.hist + (size_t)l * dn * S.n : nullptr;
+  v.row_expo = S.row_expo + (size_t)l * S.d;
+  v.irs      = S.irs + (size_t)l * S.d;
+  v.hslot    = S.hslot + (size_t)l * S.d;
+  v.meta     = S.meta + (size_t)l * HM_STRIDE;
+  return v;
+}
+
+__device__ inline bool hsetup(const HBatch &S, HView &v, double *&sR, double *&sP, int &lane)
+{
+  extern __shared__ __align__(16) double smem[];
+  const int w = threadIdx.x >> 5;
+  lane        = threadIdx.x & 31;
+  const int l = blockIdx.x * (blockDim.x >> 5) + w;
+  const size_t npad = (size_t)(S.n + 1) & ~(size_t)1;
+  sR = smem + (size_t)w * 2 * npad;
+  sP = sR + npad;
+  if (l >= S.B)
+    return false;
+  v = hview(S, l);
+  return true;
+}
+
+// ascending chain over products already in shared memory: r = p[beg]; r += p[k] ... (numvect.h:385-395), lane 0, result
+// broadcast.  The products themselves were formed one per lane (each a correctly rounded multiply).
+__device__ inline double chain_sum(const double *p, int beg, int end, int lane)
+{
+  double r = 0.0;
+  if (lane == 0)
+  {
+    r = p[beg];
+    for (int k = beg + 1; k < end; k++)
+      r = __dadd_rn(r, p[k]);
+  }
+  return __shfl_sync(FULLM, r, 0);
+}
+
+// refresh_R_bf(i), householder.cpp:186-245
+__device__ inline void w_refresh_R_bf(const HView &v, int i, double *sP, int lane)
+{
+  const int n = v.n;
+  int nc      = max(v.meta[HM_NKC], v.irs[i]);
+  __syncwarp();
+  if (lane == 0)
+    v.meta[HM_NKC] = nc;
+  const int64_t *brow = v.b + (size_t)i * v.ldb;
+  double *bfr = v.bf + (size_t)i * n, *Rr = v.R + (size_t)i * n;
+  int mx = 0;
+  if (v.row_expo_en)
+  {
+    mx = INT_MIN;
+    for (int c = lane; c < nc; c += 32)
+    {
+      int e;
+      (void)frexp((double)brow[c], &e);
+      mx = max(mx, e);
+    }
+    for (int o = 16; o; o >>= 1)
+      mx = max(mx, __shfl_xor_sync(FULLM, mx, o));
+  }
+  for (int c = lane; c < n; c += 32)
+  {
+    double f = 0.0;
+    if (c < nc)
+    {
+      if (v.row_expo_en)
+      {
+        int e;
+        const double m = frexp((double)brow[c], &e);
+        f              = ldexp(m, e - mx);
+      }
+      else
+        f = (double)brow[c];
+    }
+    bfr[c] = f;
+    Rr[c]  = f;
+    if (c < nc)
+      sP[c] = __dmul_rn(f, f);
+  }
+  __syncwarp();
+  const double ns = chain_sum(sP, 0, nc, lane);  // norm_square_b_row, householder.h:538-551
+  if (lane == 0)
+  {
+    if (v.row_expo_en)
+      v.row_expo[i] = mx;
+    v.nsb[i]  = ns;
+    v.ensb[i] = v.row_expo_en ? 2L * mx : 0L;
+  }
+  __syncwarp();
+}
+
+// refresh_R(i), householder.cpp:247-261
+__device__ inline void w_refresh_R(const HView &v, int i, int lane)
+{
+  const int n = v.n, nc = v.meta[HM_NKC];
+  const double *bfr = v.bf + (size_t)i * n;
+  double *Rr        = v.R + (size_t)i * n;
+  for (int c = lane; c < n; c += 32)
+    Rr[c] = (c < nc) ? bfr[c] : 0.0;
+  __syncwarp();
+}
+
+// update_R_last(i), householder.cpp:27-146 (default branch, no precomputed inverse)
+__device__ inline void w_update_R_last(const HView &v, int i, double *sP, int lane)
+{
+  const int n = v.n;
+  double *Rr = v.R + (size_t)i * n, *Vr = v.V + (size_t)i * n;
+  const double rii = Rr[i];
+  const double sg  = (rii < 0) ? -1.0 : 1.0;
+  double f3        = 0.0;
+  if (i + 1 < n)
+  {
+    for (int k = i + 1 + lane; k < n; k += 32)
+      sP[k] = __dmul_rn(Rr[k], Rr[k]);
+    __syncwarp();
+    f3 = chain_sum(sP, i + 1, n, lane);
+  }
+  double f1 = __dadd_rn(__dmul_rn(rii, rii), f3);
+  if (f1 != 0.0)
+  {
+    const double f2 = sqrt(f1);  // IEEE sqrt (correctly rounded, as ::sqrt)
+    double f0       = __dmul_rn(sg, f2);
+    f1              = __dadd_rn(rii, f0);
+    f3              = -f3;
+    f3              = __ddiv_rn(f3, f1);
+    if (f3 != 0.0)
+    {
+      f0 = -f0;
+      f0 = __dmul_rn(f0, f3);
+      f0 = sqrt(f0);
+      for (int k = i + 1 + lane; k < n; k += 32)
+        Vr[k] = __ddiv_rn(Rr[k], f0);
+      if (lane == 0)
+      {
+        Vr[i] = __ddiv_rn(f3, f0);
+        Rr[i] = f2;
+      }
+    }
+    else
+    {
+      for (int k = i + 1 + lane; k < n; k += 32)
+        Vr[k] = 0.0;
+      if (lane == 0)
+      {
+        Vr[i] = 0.0;
+        if (rii < 0)
+          Rr[i] = -rii;
+      }
+    }
+  }
+  else
+  {
+    for (int k = i + 1 + lane; k < n; k += 32)
+      Vr[k] = 0.0;
+    if (lane == 0)
+    {
+      Rr[i] = 0.0;
+      Vr[i] = 0.0;
+    }
+  }
+  if (lane == 0)
+  {
+    v.sigma[i] = sg;
+    v.meta[HM_NKR] += 1;
+  }
+  __syncwarp();
+}
+
+// update_R(i, last_j), householder.cpp:151-184
+__device__ inline void w_update_R(const HView &v, int i, int last_j, double *sR, double *sP, int lane)
+{
+  const int n = v.n;
+  if (!v.meta[HM_UPDATED])
+  {
+    double *Rr = v.R + (size_t)i * n;
+    for (int k = lane; k < n; k += 32)
+      sR[k] = Rr[k];
+    __syncwarp();
+    double *hrow = v.keep_hist ? v.hist + (size_t)v.hslot[i] * n * n : nullptr;
+    for (int j = 0; j < i; j++)
+    {
+      const double *Vj = v.V + (size_t)j * n;
+      // products V(j,k) * R(i,k), k = j..n-1 (coalesced row sweep), then the ordered sum
+      double vk[8];
+      int cnt = 0;
+      for (int k = j + lane; k < n; k += 32, cnt++)
+      {
+        const double x = Vj[k];
+        if (cnt < 8)
+          vk[cnt] = x;
+        sP[k] = __dmul_rn(x, sR[k]);
+      }
+      __syncwarp();
+      double f0 = chain_sum(sP, j, n, lane);
+      f0        = -f0;
+      // R(i,k) += V(j,k) * f0  (element-wise, order irrelevant), then R(i,j) *= sigma[j]
+      cnt = 0;
+      for (int k = j + lane; k < n; k += 32, cnt++)
+      {
+        const double x = (cnt < 8) ? vk[cnt] : Vj[k];
+        double r       = __dadd_rn(sR[k], __dmul_rn(x, f0));
+        if (k == j)
+          r = __dmul_rn(v.sigma[j], r);
+        sR[k] = r;
+        if (hrow)
+          hrow[(size_t)j * n + k] = r;  // R_history[i][j][k] = R(i,k), k >= j
+      }
+      __syncwarp();
+    }
+    for (int k = lane; k < n; k += 32)
+      Rr[k] = sR[k];
+    __syncwarp();
+    if (last_j)
+      w_update_R_last(v, i, sP, lane);
+  }
+}
+
+__device__ inline long hfexpo(double x) { return (long)ilogb(x) + 1; }
+
+// size_reduce(k, end, start), householder.cpp:403-451 with row_addmul_we, :522-559
+__device__ inline bool w_size_reduce(const HView &v, int k, int sr_end, int sr_start, int lane)
+{
+  const int n = v.n, nc = v.meta[HM_NKC];
+  double *Rk          = v.R + (size_t)k * n;
+  unsigned long long *bk = (unsigned long long *)(v.b + (size_t)k * v.ldb);
+  bool reduced = false;
+  for (int i = sr_end - 1; i >= sr_start; i--)
+  {
+    const double *Ri = v.R + (size_t)i * n;
+    double f         = __ddiv_rn(Rk[i], Ri[i]);
+    const long de    = (long)(v.row_expo[k] - v.row_expo[i]);
+    if (!(hfexpo(f) + de >= 53))
+      f = ldexp(rint(ldexp(f, (int)de)), (int)-de);  // rnd_we, nr_FP_d.inl:226-233
+    f = -f;
+    if (f != 0.0)
+    {
+      long expo = 0;
+      const long e = hfexpo(f) + de - 63;  // get_si_exp_we, nr_FP_d.inl:46-53
+      expo         = e > 0 ? e : 0;
+      const unsigned long long lx = (unsigned long long)(long)ldexp(f, (int)(de - expo));
+      const unsigned long long *bi = (const unsigned long long *)(v.b + (size_t)i * v.ldb);
+      for (int c = lane; c < nc; c += 32)
+      {
+        unsigned long long t = bi[c] * lx;
+        if (expo)
+          t = expo >= 64 ? 0ull : (t << expo);
+        bk[c] += t;
+      }
+      for (int c = lane; c < i; c += 32)
+      {
+        if (f == 1.0)
+          Rk[c] = __dadd_rn(Rk[c], Ri[c]);
+        else if (f == -1.0)
+          Rk[c] = __dsub_rn(Rk[c], Ri[c]);
+        else
+          Rk[c] = __dadd_rn(Rk[c], __dmul_rn(Ri[c], f));
+      }
+      reduced = true;
+      __syncwarp();
+    }
+  }
+  if (reduced && lane == 0 && k < v.meta[HM_NKR])
+    v.meta[HM_NKR] = k;  // invalidate_row(k)
+  __syncwarp();
+  return reduced;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+__global__ void hk_init(HBatch S)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (!hsetup(S, v, sR, sP, lane))
+    return;
+  if (lane < HM_STRIDE)
+    v.meta[lane] = 0;
+  for (int i = 0; i < v.d; i++)
+  {
+    int last = 0;
+    for (int c = lane; c < v.n; c += 32)
+      if (v.b[(size_t)i * v.ldb + c] != 0)
+        last = c + 1;
+    for (int o = 16; o; o >>= 1)
+      last = max(last, __shfl_xor_sync(FULLM, last, o));
+    if (lane == 0)
+    {
+      v.irs[i]      = max(last, 1);
+      v.row_expo[i] = 0;
+      v.hslot[i]    = i;
+      v.sigma[i]    = 0.0;
+      v.nsb[i]      = 0.0;
+      v.ensb[i]     = 0;
+    }
+  }
+}
+
+__global__ void hk_pack_b(HBatch S, const int64_t *src, int dir)
+{
+  const int l      = blockIdx.y;
+  int64_t *b       = S.b + (size_t)l * S.d * S.ldb;
+  const size_t tot = (size_t)S.d * S.n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x)
+  {
+    const int i = (int)(t / S.n), c = (int)(t % S.n);
+    if (dir == 0)
+      b[(size_t)i * S.ldb + c] = src[(size_t)l * tot + t];
+    else
+      ((int64_t *)src)[(size_t)l * tot + t] = b[(size_t)i * S.ldb + c];
+  }
+}
+
+__global__ void hk_refresh_R_bf(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane))
+    w_refresh_R_bf(v, i, sP, lane);
+}
+__global__ void hk_refresh_R(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane))
+    w_refresh_R(v, i, lane);
+}
+__global__ void hk_update_R(HBatch S, int i, int last_j)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane))
+    w_update_R(v, i, last_j, sR, sP, lane);
+}
+__global__ void hk_update_R_last(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane))
+    w_update_R_last(v, i, sP, lane);
+}
+__global__ void hk_size_reduce(HBatch S, int k, int e, int st, int *reduced)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (!hsetup(S, v, sR, sP, lane))
+    return;
+  const bool r = w_size_reduce(v, k, e, st, lane);
+  if (reduced && lane == 0)
+    reduced[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = r ? 1 : 0;
+}
+// swap(i, j), householder.cpp:372-398
+__global__ void hk_swap(HBatch S, int i, int j)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (!hsetup(S, v, sR, sP, lane))
+    return;
+  if (lane == 0 && i < v.meta[HM_NKR])
+    v.meta[HM_NKR] = i;  // invalidate_row(i)
+  for (int c = lane; c < v.n; c += 32)
+  {
+    const int64_t t = v.b[(size_t)i * v.ldb + c];
+    v.b[(size_t)i * v.ldb + c] = v.b[(size_t)j * v.ldb + c];
+    v.b[(size_t)j * v.ldb + c] = t;
+    const double f = v.bf[(size_t)i * v.n + c];
+    v.bf[(size_t)i * v.n + c] = v.bf[(size_t)j * v.n + c];
+    v.bf[(size_t)j * v.n + c] = f;
+  }
+  if (lane == 0)
+  {
+    double t = v.sigma[i];
+    v.sigma[i] = v.sigma[j], v.sigma[j] = t;
+    if (v.row_expo_en)
+    {
+      int e = v.row_expo[i];
+      v.row_expo[i] = v.row_expo[j], v.row_expo[j] = e;
+    }
+    int q = v.irs[i];
+    v.irs[i] = v.irs[j], v.irs[j] = q;
+    q = v.hslot[i];
+    v.hslot[i] = v.hslot[j], v.hslot[j] = q;  // iter_swap(R_history.begin()+i, +j): pointer swap
+    t = v.nsb[i];
+    v.nsb[i] = v.nsb[j], v.nsb[j] = t;
+    long le = v.ensb[i];
+    v.ensb[i] = v.ensb[j], v.ensb[j] = le;
+  }
+}
+// recover_R(i), householder.h:597-608
+__global__ void hk_recover_R(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (!hsetup(S, v, sR, sP, lane))
+    return;
+  const int n = v.n;
+  const double *hrow = v.hist + (size_t)v.hslot[i] * n * n;
+  double *Rr = v.R + (size_t)i * n;
+  for (int k = lane; k < n; k += 32)
+    Rr[k] = (k < i - 1) ? hrow[(size_t)k * n + k] : hrow[(size_t)(i - 1) * n + k];
+  if (lane == 0)
+    v.meta[HM_UPDATED] = 1;
+}
+__global__ void hk_set_updated(HBatch S, int val)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < S.B)
+    S.meta[(size_t)l * HM_STRIDE + HM_UPDATED] = val;
+}
+
+}  // namespace
+
+struct b200hh
+{
+  HBatch S;
+  int device;
+  cudaStream_t stream;
+  size_t smem;
+  int *d_red;
+  std::vector<void *> allocs;
+};
+
+template <class T> static int hh_alloc(b200hh *h, T **p, size_t count)
+{
+  void *q = nullptr;
+  if (cudaMalloc(&q, count * sizeof(T) + 256) != cudaSuccess)
+  {
+    g_err = "cudaMalloc failed";
+    cudaGetLastError();
+    return B200HH_ENOMEM;
+  }
+  h->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+static int hgrid(const b200hh *h) { return (h->S.B + HW - 1) / HW; }
+
+extern "C" {
+
+const char *b200hh_last_error(void) { return g_err.c_str(); }
+
+int b200hh_create(b200hh_t **out, int batch, int d, int n, int flags, int device, int keep_history)
+{
+  if (!out || batch <= 0 || d <= 0 || n <= 0)
+    return B200HH_EINVAL;
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd <= device)
+  {
+    cudaGetLastError();
+    g_err = "b200hh_create: no CUDA device (this library has no CPU fallback)";
+    return B200HH_ENODEV;
+  }
+  CKH(cudaSetDevice(device));
+  b200hh *h = new b200hh();
+  h->device = device;
+  HBatch &S = h->S;
+  S.B = batch, S.d = d, S.n = n, S.ldb = (n + 1) & ~1, S.row_expo_en = (flags & B200HH_ROW_EXPO) ? 1 : 0;
+  S.keep_hist     = keep_history ? 1 : 0;
+  const size_t dn = (size_t)d * n;
+  int rc          = 0;
+  rc |= hh_alloc(h, &S.b, (size_t)batch * d * S.ldb);
+  rc |= hh_alloc(h, &S.bf, batch * dn);
+  rc |= hh_alloc(h, &S.R, batch * dn);
+  rc |= hh_alloc(h, &S.V, batch * dn);
+  rc |= hh_alloc(h, &S.sigma, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.nsb, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.ensb, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.row_expo, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.irs, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.hslot, (size_t)batch * d);
+  rc |= hh_alloc(h, &S.meta, (size_t)batch * HM_STRIDE);
+  rc |= hh_alloc(h, &h->d_red, (size_t)batch);
+  S.hist = nullptr;
+  if (!rc && keep_history)
+    rc |= hh_alloc(h, &S.hist, batch * dn * n);
+  if (rc)
+  {
+    for (void *p : h->allocs)
+      cudaFree(p);
+    delete h;
+    return B200HH_ENOMEM;
+  }
+  CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->smem = (size_t)HW * 2 * ((n + 1) & ~1) * sizeof(double);
+  const void *fns[] = {(const void *)hk_init,        (const void *)hk_refresh_R_bf, (const void *)hk_refresh_R,
+                       (const void *)hk_update_R,    (const void *)hk_update_R_last, (const void *)hk_size_reduce,
+                       (const void *)hk_swap,        (const void *)hk_recover_R};
+  for (const void *f : fns)
+    CKH(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CKH(cudaMemsetAsync(S.b, 0, (size_t)batch * d * S.ldb * 8, h->stream));
+  CKH(cudaMemsetAsync(S.bf, 0, batch * dn * 8, h->stream));
+  CKH(cudaMemsetAsync(S.R, 0, batch * dn * 8, h->stream));
+  CKH(cudaMemsetAsync(S.V, 0, batch * dn * 8, h->stream));
+  CKH(cudaMemsetAsync(S.meta, 0, (size_t)batch * HM_STRIDE * 4, h->stream));
+  CKH(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+void b200hh_destroy(b200hh_t *h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamDestroy(h->stream);
+  for (void *p : h->allocs)
+    cudaFree(p);
+  delete h;
+}
+
+int b200hh_set_basis(b200hh_t *h, const int64_t *b)
+{
+  if (!h || !b)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->S.B * h->S.d * h->S.n;
+  int64_t *tmp     = nullptr;
+  CKH(cudaMalloc(&tmp, cnt * 8));
+  CKH(cudaMemcpyAsync(tmp, b, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+  dim3 g(32, h->S.B);
+  hk_pack_b<<<g, 256, 0, h->stream>>>(h->S, tmp, 0);
+  hk_init<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S);
+  CKH(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+int b200hh_get_basis(b200hh_t *h, int64_t *b)
+{
+  if (!h || !b)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->S.B * h->S.d * h->S.n;
+  int64_t *tmp     = nullptr;
+  CKH(cudaMalloc(&tmp, cnt * 8));
+  dim3 g(32, h->S.B);
+  hk_pack_b<<<g, 256, 0, h->stream>>>(h->S, tmp, 1);
+  CKH(cudaMemcpyAsync(b, tmp, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  CKH(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+#define HH_CALL(cond, launch)                    \
+  if (!h || !(cond))                             \
+    return B200HH_EINVAL;                        \
+  CKH(cudaSetDevice(h->device));                 \
+  launch;                                        \
+  CKH(cudaGetLastError());                       \
+  return 0;
+
+int b200hh_refresh_R_bf(b200hh_t *h, int i)
+{
+  HH_CALL(i >= 0 && i < h->S.d, (hk_refresh_R_bf<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i)))
+}
+int b200hh_refresh_R(b200hh_t *h, int i)
+{
+  HH_CALL(i >= 0 && i < h->S.d, (hk_refresh_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i)))
+}
+int b200hh_update_R(b200hh_t *h, int i, int last_j)
+{
+  HH_CALL(i >= 0 && i < h->S.d, (hk_update_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i, last_j)))
+}
+int b200hh_update_R_last(b200hh_t *h, int i)
+{
+  HH_CALL(i >= 0 && i < h->S.d, (hk_update_R_last<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i)))
+}
+int b200hh_swap(b200hh_t *h, int i, int j)
+{
+  HH_CALL(i >= 0 && i < j && j < h->S.d, (hk_swap<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i, j)))
+}
+int b200hh_recover_R(b200hh_t *h, int i)
+{
+  HH_CALL(i >= 1 && i < h->S.d && h->S.keep_hist, (hk_recover_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i)))
+}
+int b200hh_set_updated_R_false(b200hh_t *h)
+{
+  HH_CALL(true, (hk_set_updated<<<(h->S.B + 127) / 128, 128, 0, h->stream>>>(h->S, 0)))
+}
+
+int b200hh_size_reduce(b200hh_t *h, int k, int e, int st, int *reduced)
+{
+  if (!h || k <= 0 || k >= h->S.d || e > k || st < 0 || st > e)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  hk_size_reduce<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, k, e, st, h->d_red);
+  if (reduced)
+  {
+    CKH(cudaMemcpyAsync(reduced, h->d_red, sizeof(int) * h->S.B, cudaMemcpyDeviceToHost, h->stream));
+    CKH(cudaStreamSynchronize(h->stream));
+  }
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+int b200hh_get_state(b200hh_t *h, double *R, double *V, double *bf, double *sigma, double *norm_square_b,
+                     int64_t *row_expo, int64_t *expo_norm_square_b, int *meta)
+{
+  if (!h)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  const HBatch &S = h->S;
+  const size_t dn = (size_t)S.B * S.d * S.n, bd = (size_t)S.B * S.d;
+  if (R)
+    CKH(cudaMemcpyAsync(R, S.R, dn * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (V)
+    CKH(cudaMemcpyAsync(V, S.V, dn * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (bf)
+    CKH(cudaMemcpyAsync(bf, S.bf, dn * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma)
+    CKH(cudaMemcpyAsync(sigma, S.sigma, bd * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (norm_square_b)
+    CKH(cudaMemcpyAsync(norm_square_b, S.nsb, bd * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (expo_norm_square_b)
+    CKH(cudaMemcpyAsync(expo_norm_square_b, S.ensb, bd * 8, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<int> re, m;
+  if (row_expo)
+  {
+    re.resize(bd);
+    CKH(cudaMemcpyAsync(re.data(), S.row_expo, bd * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (meta)
+  {
+    m.resize((size_t)S.B * HM_STRIDE);
+    CKH(cudaMemcpyAsync(m.data(), S.meta, m.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CKH(cudaStreamSynchronize(h->stream));
+  if (row_expo)
+    for (size_t t = 0; t < bd; t++)
+      row_expo[t] = re[t];
+  if (meta)
+    for (int l = 0; l < S.B; l++)
+      for (int q = 0; q < 3; q++)
+        meta[3 * l + q] = m[(size_t)l * HM_STRIDE + q];
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+int b200hh_time_update_R(b200hh_t *h, int i, int reps, float *ms_update_mean)
+{
+  if (!h || !ms_update_mean || reps <= 0 || i < 0 || i >= h->S.d)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+  for (auto &e : ev)
+    CKH(cudaEventCreate(&e));
+  for (int r = 0; r < reps; r++)
+  {
+    hk_refresh_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i);
+    CKH(cudaEventRecord(ev[2 * r], h->stream));
+    hk_update_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i, 0);
+    CKH(cudaEventRecord(ev[2 * r + 1], h->stream));
+  }
+  CKH(cudaStreamSynchronize(h->stream));
+  double tot = 0;
+  for (int r = 0; r < reps; r++)
+  {
+    float ms = 0;
+    CKH(cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]));
+    tot += ms;
+  }
+  for (auto &e : ev)
+    cudaEventDestroy(e);
+  *ms_update_mean = (float)(tot / reps);
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+int b200hh_sync(b200hh_t *h)
+{
+  if (!h)
+    return B200HH_EINVAL;
+  CKH(cudaSetDevice(h->device));
+  CKH(cudaStreamSynchronize(h->stream));
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -284,3 +284,108 @@ def read_enum_records(path):
             off += 8 * d
         out.append(rec)
     return out
+
+
+# ---- Householder ----------------------------------------------------------------------------------------
+
+class _OHH(C.Structure):
+    _fields_ = [("d", C.c_int), ("n", C.c_int), ("enable_row_expo", C.c_int), ("n_known_rows", C.c_int),
+                ("n_known_cols", C.c_int), ("updated_R", C.c_int),
+                ("b", C.POINTER(C.c_int64)), ("bf", C.POINTER(C.c_double)), ("R", C.POINTER(C.c_double)),
+                ("V", C.POINTER(C.c_double)), ("sigma", C.POINTER(C.c_double)), ("hist", C.POINTER(C.c_double)),
+                ("row_expo", C.POINTER(C.c_int64)), ("init_row_size", C.POINTER(C.c_int)),
+                ("norm_square_b", C.POINTER(C.c_double)), ("expo_norm_square_b", C.POINTER(C.c_int64))]
+
+
+HOUSEHOLDER_ROW_EXPO, HOUSEHOLDER_OP_FORCE_LONG = 1, 4  # householder.h:26-32
+
+
+class OracleHouseholder:
+    """MatHouseholder<Z_NR<long>, FP_NR<double>> restated in C (oracle/hh_oracle.c); reference method names."""
+
+    def __init__(self, b, flags=HOUSEHOLDER_ROW_EXPO | HOUSEHOLDER_OP_FORCE_LONG):
+        L = lib()
+        b = np.ascontiguousarray(b, dtype=np.int64)
+        self.d, self.n = b.shape
+        L.ohh_create.restype = C.POINTER(_OHH)
+        L.ohh_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]
+        for f, at in [("ohh_destroy", [C.POINTER(_OHH)]), ("ohh_refresh_R_bf", [C.POINTER(_OHH), C.c_int]),
+                      ("ohh_refresh_R", [C.POINTER(_OHH), C.c_int]),
+                      ("ohh_update_R", [C.POINTER(_OHH), C.c_int, C.c_int]),
+                      ("ohh_update_R_last", [C.POINTER(_OHH), C.c_int]),
+                      ("ohh_size_reduce", [C.POINTER(_OHH), C.c_int, C.c_int, C.c_int]),
+                      ("ohh_swap", [C.POINTER(_OHH), C.c_int, C.c_int]),
+                      ("ohh_recover_R", [C.POINTER(_OHH), C.c_int]),
+                      ("ohh_set_updated_R_false", [C.POINTER(_OHH)])]:
+            getattr(L, f).argtypes = at
+        self._p = L.ohh_create(self.d, self.n, b.ctypes.data_as(C.POINTER(C.c_int64)), flags)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().ohh_destroy(self._p)
+            self._p = None
+
+    def refresh_R_bf(self, i):
+        lib().ohh_refresh_R_bf(self._p, i)
+
+    def refresh_R(self, i):
+        lib().ohh_refresh_R(self._p, i)
+
+    def update_R(self, i, last_j=True):
+        lib().ohh_update_R(self._p, i, 1 if last_j else 0)
+
+    def update_R_last(self, i):
+        lib().ohh_update_R_last(self._p, i)
+
+    def size_reduce(self, k, end, start=0):
+        return bool(lib().ohh_size_reduce(self._p, k, end, start))
+
+    def swap(self, i, j):
+        lib().ohh_swap(self._p, i, j)
+
+    def recover_R(self, i):
+        lib().ohh_recover_R(self._p, i)
+
+    def set_updated_R_false(self):
+        lib().ohh_set_updated_R_false(self._p)
+
+    def state(self):
+        m = self._p.contents
+        d, n = self.d, self.n
+
+        def arr(ptr, shape, dt):
+            cnt = int(np.prod(shape))
+            return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt).reshape(shape).copy()
+        return dict(d=d, n=n, n_known_rows=m.n_known_rows, n_known_cols=m.n_known_cols, updated_R=m.updated_R,
+                    row_expo=arr(m.row_expo, (d,), np.int64), sigma=arr(m.sigma, (d,), np.float64),
+                    norm_square_b=arr(m.norm_square_b, (d,), np.float64),
+                    expo_norm_square_b=arr(m.expo_norm_square_b, (d,), np.int64),
+                    bf=arr(m.bf, (d, n), np.float64), R=arr(m.R, (d, n), np.float64),
+                    V=arr(m.V, (d, n), np.float64), b=arr(m.b, (d, n), np.int64))
+
+
+def read_hh_dumps(path):
+    raw = open(path, "rb").read()
+    off, out = 0, []
+    while off < len(raw):
+        hdr = np.frombuffer(raw, np.int32, 6, off)
+        off += 24
+        assert hdr[0] == 0x48483030
+        d, n = int(hdr[1]), int(hdr[2])
+        rec = dict(d=d, n=n, n_known_rows=int(hdr[3]), n_known_cols=int(hdr[4]), updated_R=int(hdr[5]))
+
+        def take(dt, shape):
+            nonlocal off
+            a = np.frombuffer(raw, dt, int(np.prod(shape)), off).reshape(shape).copy()
+            off += a.nbytes
+            return a
+        rec["row_expo"] = take(np.int64, (d,))
+        rec["sigma"] = take(np.float64, (d,))
+        rec["norm_square_b"] = take(np.float64, (d,))
+        rec["expo_norm_square_b"] = take(np.int64, (d,))
+        rec["bf"] = take(np.float64, (d, n))
+        rec["R"] = take(np.float64, (d, n))
+        rec["V"] = take(np.float64, (d, n))
+        rec["b"] = take(np.int64, (d, n))
+        out.append(rec)
+    return out

@@ -11,15 +11,30 @@
  *   int64 row_expo[d]; int32 gso_valid_cols[d]; int32 init_row_size[d]
  *   f64 bf[d*n]; f64 gf[d*d]; f64 mu[d*d]; f64 r[d*d]; int64 b[d*n] (ztype long only, else absent)
  */
-#include <fplll.h>
+#include <algorithm>
+#include <array>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
+#include <map>
 #include <memory>
+#include <numeric>
+#include <set>
 #include <sstream>
+#include <string>
 #include <thread>
+#include <vector>
+/* the probe reads private state of the reference classes (MatHouseholder::R, V, sigma ...): same object layout,
+   access checks off — standard headers are already included above so only fplll's own declarations are affected */
+#define private public
+#define protected public
+#include <fplll.h>
+#undef private
+#undef protected
 
 using namespace fplll;
 using namespace std;
@@ -294,6 +309,47 @@ static void run_enum(GsoL &m, int first, int last, double factor, const string &
          (unsigned long long)tot, sec);
 }
 
+/* ---- Householder probes: MatHouseholder<Z_NR<long>, FP_NR<double>> over the current long matrix --------------
+ * hh FLAGS | hh_refresh_R_bf I | hh_refresh_R I | hh_update_R I LASTJ | hh_update_R_last I | hh_size_reduce K END START
+ * | hh_swap I J | hh_recover_R I | hh_set_updated_R_false | hh_dump FILE
+ * dump (appended): int32 magic 0x48483030, d, n, n_known_rows, n_known_cols, updated_R; int64 row_expo[d];
+ *   f64 sigma[d]; f64 norm_square_b[d]; int64 expo_norm_square_b[d]; f64 bf[d*n]; f64 R[d*n]; f64 V[d*n]; int64 b[d*n]
+ */
+typedef MatHouseholder<Z_NR<long>, FP_NR<double>> HhL;
+static unique_ptr<HhL> hh;
+static void hh_dump(const char *path)
+{
+  FILE *f = fopen(path, "ab");
+  int d = hh->d, n = hh->n;
+  int32_t hdr[6] = {0x48483030, d, n, hh->n_known_rows, hh->n_known_cols, (int)hh->updated_R};
+  wr(f, hdr, 6);
+  vector<int64_t> re(d), en(d);
+  vector<double> sg(d), nb(d);
+  for (int i = 0; i < d; i++)
+  {
+    re[i] = hh->row_expo[i];
+    sg[i] = hh->sigma[i].get_d();
+    nb[i] = hh->norm_square_b[i].get_d();
+    en[i] = hh->expo_norm_square_b[i];
+  }
+  wr(f, re.data(), d), wr(f, sg.data(), d), wr(f, nb.data(), d), wr(f, en.data(), d);
+  vector<double> buf((size_t)d * n);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      buf[(size_t)i * n + j] = hh->bf(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      buf[(size_t)i * n + j] = hh->R(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      buf[(size_t)i * n + j] = hh->V(i, j).get_d();
+  wr(f, buf.data(), buf.size());
+  fclose(f);
+  dump_b_long(path);
+}
+
 int main(int argc, char **argv)
 {
   string line;
@@ -542,6 +598,33 @@ int main(int argc, char **argv)
       }
       set_external_enumerator(bundled);
       printf("bkz status=%d sec=%.6f\n", st, now() - t0);
+    }
+    else if (c == "hh")
+    {
+      int fl;
+      is >> fl;
+      hh.reset(new HhL(Bl, Ul, UTl, fl));
+    }
+    else if (c == "hh_refresh_R_bf") { int i; is >> i; hh->refresh_R_bf(i); }
+    else if (c == "hh_refresh_R") { int i; is >> i; hh->refresh_R(i); }
+    else if (c == "hh_update_R") { int i, l; is >> i >> l; hh->update_R(i, l != 0); }
+    else if (c == "hh_update_R_last") { int i; is >> i; hh->update_R_last(i); }
+    else if (c == "hh_size_reduce") { int k, e, st; is >> k >> e >> st; printf("hh_size_reduce %d\n", (int)hh->size_reduce(k, e, st)); }
+    else if (c == "hh_swap") { int i, j; is >> i >> j; hh->swap(i, j); }
+    else if (c == "hh_recover_R") { int i; is >> i; hh->recover_R(i); }
+    else if (c == "hh_set_updated_R_false") { hh->set_updated_R_false(); }
+    else if (c == "hh_dump") { string p; is >> p; hh_dump(p.c_str()); }
+    else if (c == "hlll_long")
+    {
+      /* hlll_reduction on the long matrix: HLLLReduction<Z_NR<long>,FP_NR<double>> with ROW_EXPO|OP_FORCE_LONG
+         (wrapper.cpp:789-806 for the mpz type) */
+      double delta, eta, theta, cc;
+      is >> delta >> eta >> theta >> cc;
+      HhL m(Bl, Ul, UTl, HOUSEHOLDER_ROW_EXPO | HOUSEHOLDER_OP_FORCE_LONG);
+      HLLLReduction<Z_NR<long>, FP_NR<double>> red(m, delta, eta, theta, cc, LLL_DEFAULT);
+      double t0 = now();
+      red.hlll();
+      printf("hlll_long status=%d sec=%.6f\n", red.get_status(), now() - t0);
     }
     else if (c == "time_update_row")
     {

@@ -7,7 +7,8 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADERS = {"b200gso.h": "libb200gso.so", "b200enum.h": "libb200enum.so", "b200bkz.h": "libb200bkz.so"}
+HEADERS = {"b200gso.h": "libb200gso.so", "b200enum.h": "libb200enum.so", "b200bkz.h": "libb200bkz.so",
+           "b200hh.h": "libb200hh.so"}
 
 
 @pytest.mark.parametrize("hdr,libname", sorted(HEADERS.items()))

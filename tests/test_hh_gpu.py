@@ -1,0 +1,86 @@
+"""GPU parity tests of the device Householder state (include/b200hh.h) against the oracle restatement, which is itself
+pinned bit-exactly to the reference (tests/test_hh_oracle.py).  Same HLLL-like call order as hlll.cpp:49-171."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _hlll_like_ops(d):
+    ops = [("refresh_R_bf", 0), ("update_R_last", 0), ("refresh_R_bf", 1)]
+    k, kmax = 1, 1
+    for step in range(3 * d):
+        ops += [("update_R", k, 0), ("size_reduce", k, k, 0), ("refresh_R_bf", k), ("update_R", k, 0), ("check",)]
+        if step % 3 != 2 or k == 1:
+            ops += [("update_R_last", k)]
+            k += 1
+            if k >= d:
+                break
+            ops += [("refresh_R_bf", k)] if k > kmax else [("refresh_R", k)]
+            kmax = max(kmax, k)
+        else:
+            ops += [("swap", k - 1, k)]
+            k -= 1
+            ops += [("recover_R", k), ("check",), ("set_updated_R_false",)]
+    ops.append(("check",))
+    return ops, kmax
+
+
+@pytest.mark.parametrize("seed,d,n,bits,batch", [(1, 10, 10, 20, 1), (2, 24, 30, 12, 3), (3, 40, 40, 30, 2),
+                                                 (4, 70, 75, 10, 2)])
+def test_hlll_like_sequence_bit_exact(seed, d, n, bits, batch):
+    from fplll_b200.householder import MatHouseholder
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-(1 << bits), 1 << bits, size=(batch, d, n), dtype=np.int64)
+    ops, kmax = _hlll_like_ops(d)
+    md = MatHouseholder(b, 5)
+    mos = [O.OracleHouseholder(b[l], 5) for l in range(batch)]
+    checks = 0
+    for op in ops:
+        if op[0] == "check":
+            st = md.state()
+            for l, mo in enumerate(mos):
+                s = mo.state()
+                nk = s["n_known_rows"]
+                what = "seed %d lattice %d check %d" % (seed, l, checks)
+                assert st["n_known_rows"][l] == nk and st["n_known_cols"][l] == s["n_known_cols"], what
+                assert np.array_equal(st["b"][l], s["b"]), what + " b"
+                rows = min(d, kmax + 1)
+                for k in ["row_expo", "expo_norm_square_b"]:
+                    assert np.array_equal(st[k][l][:rows], s[k][:rows]), what + " " + k
+                for k in ["sigma", "norm_square_b"]:
+                    assert H.eq_f64(st[k][l][:nk], s[k][:nk]), what + " " + k
+                assert H.eq_f64(st["bf"][l][:rows], s["bf"][:rows]), what + " bf"
+                assert H.eq_f64(st["R"][l][:rows], s["R"][:rows]), what + " R"
+                assert H.eq_f64(st["V"][l][:nk], s["V"][:nk]), what + " V"
+            checks += 1
+        else:
+            r = getattr(md, op[0])(*op[1:])
+            for l, mo in enumerate(mos):
+                ro = getattr(mo, op[0])(*op[1:])
+                if op[0] == "size_reduce":
+                    assert bool(r[l]) == bool(ro)
+    assert checks > 5
+
+
+def test_full_qr_matches_gso_relation():
+    """tests/test_gso.cpp:101-152 on the device R."""
+    from fplll_b200.householder import MatHouseholder
+    b = H.gold("bkz_q60.npz")["b_in"]
+    d = b.shape[0]
+    md = MatHouseholder(b, 0, keep_history=False)
+    for i in range(d):
+        md.refresh_R_bf(i)
+        md.update_R(i)
+    R = md.state()["R"][0]
+    g = O.OracleGSO(b, 0)
+    assert g.update_gso()
+    s = g.state()
+    for i in range(d):
+        assert R[i, i] > 0
+        for j in range(i):
+            assert abs(R[i, j] / R[j, j] - s["mu"][i, j]) < 1e-9 * max(1.0, abs(s["mu"][i, j]))
+            assert abs(R[i, j] * R[j, j] - s["r"][i, j]) < 1e-9 * max(1.0, abs(s["r"][i, j]))
