@@ -109,6 +109,43 @@ def cpu_reference(seconds_target=12.0):
             "us_per_call_per_thread": t / (calls / cores) * 1e6}
 
 
+def enum_extras(local):
+    """Secondary figure of the BASELINE metric's BKZ half: the device enumerator on a full-size BKZ-60 block of the
+    dim-200 knapsack basis (tests/golden/enum_r200_b60_pruned_140.npz: 5.6e8 nodes, the reference visits exactly the
+    same nodes), next to the reference's own enumerators on the host cores (oracle/_ref, bounded: one run)."""
+    import numpy as np
+    from fplll_b200 import enumeration as en
+    out = {}
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "enum_r200_b60_pruned_140.npz"))
+        en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), devices=[local])  # warm-up
+        t0 = time.perf_counter()
+        res = en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), devices=[local])
+        dt = time.perf_counter() - t0
+        n = int(res["nodes"].sum())
+        out = {"workload": "SVP enumeration, block [140,200) of LLL-reduced latticegen r 200 2000, default.json "
+                           "beta=60 pruning, radius 1.05*GH", "nodes": n, "nodes_equal_reference": n == int(z["nodes"].sum()),
+               "gpu_seconds": dt, "gpu_nodes_per_s": n / dt, "rounds": res["stats"]["n_rounds"]}
+        from oracle import oracle as O
+        if O.have_ref():
+            g = np.load(os.path.join(ROOT, "tests", "golden", "r200_lll_update_gso.npz"))
+            tmp = tempfile.mkdtemp(prefix="bench_enum_")
+            mat, pr, ob = os.path.join(tmp, "b.txt"), os.path.join(tmp, "p.txt"), os.path.join(tmp, "o.bin")
+            O.write_matrix(mat, g["b"])
+            open(pr, "w").write(" ".join(repr(float(c)) for c in z["pruning"]))
+            factor = float(z["maxdist"]) / float(z["rdiag"][0])
+            cores = os.cpu_count() or 1
+            o = O.run_ref("load %s\ntolong\ngso l 2\nupdate_gso\nset_threads %d\nenum 140 200 %r %s %s enumlib\n"
+                          % (mat, cores, factor, pr, ob), timeout=600)
+            tok = dict(t.split("=") for t in o.split("enum d=")[1].split() if "=" in t)
+            out["cpu_reference"] = {"kind": "reference enumlib", "threads": cores, "seconds": float(tok["sec"]),
+                                    "nodes": int(tok["nodes"]), "nodes_per_s": int(tok["nodes"]) / float(tok["sec"])}
+            out["speedup_vs_cpu_reference"] = float(tok["sec"]) / dt
+    except Exception as ex:  # never break the headline line
+        out["error"] = str(ex)[:300]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -117,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="lattices per GPU (0 = two full waves of the update kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the enumeration figure")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -239,6 +277,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s / a.steps * 1e3},
                 "gpu_launches": 2 * a.steps, "clocks": clocks}
+        if not a.no_extras and world == 1:
+            line["enum"] = enum_extras(local)
         if not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference()

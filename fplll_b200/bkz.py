@@ -25,6 +25,8 @@ class _Stats(C.Structure):
     _fields_ = [("status", C.c_int), ("tours", C.c_int), ("enum_nodes", C.c_uint64), ("enum_calls", C.c_long),
                 ("lll_calls", C.c_long), ("sizered_calls", C.c_long), ("sec_total", C.c_double),
                 ("sec_enum", C.c_double), ("sec_lll", C.c_double), ("sec_other", C.c_double),
+                ("sec_ops", C.c_double), ("sec_get", C.c_double), ("op_calls", C.c_long), ("ops_total", C.c_long),
+                ("get_calls", C.c_long),
                 ("r00_before", C.c_double), ("r00_after", C.c_double), ("slope_before", C.c_double),
                 ("slope_after", C.c_double)]
 

@@ -109,7 +109,10 @@ public:
   void r_exp(int i, double &mant, long &expo)
   {
     double mu;
+    const double t0 = now_s();
     GCK(b200gso_get_block(g, 0, i, 1, &mu, &mant, &expo));
+    st->sec_get += now_s() - t0;
+    st->get_calls++;
   }
   // recorded GSO calls, flushed as one kernel launch (b200gso_apply_ops)
   std::vector<b200gso_op> ops;
@@ -130,7 +133,9 @@ public:
       return;
     const double t0 = now_s();
     GCK(b200gso_apply_ops(g, ops.data(), (int)ops.size()));
-    st->sec_other += now_s() - t0;
+    st->sec_ops += now_s() - t0;
+    st->op_calls++;
+    st->ops_total += (long)ops.size();
     ops.clear();
   }
 
@@ -176,13 +181,40 @@ public:
     if (max_row - min_row < 2)
       return;
     auto below = [&](unsigned long n) { return (unsigned long)(rng() % n); };
+    // 1. permute rows.  The reference issues 4*(max_row-min_row) move_row calls; the block is re-converted and
+    // invalidated by the row_op_end below, so of all those rotations only the NET permutation of the integer rows
+    // is observable (everything a move_row leaves valid lies in columns < min_row or in rows
+    // >= max_row, which a rotation inside the block does not touch).  Simulate the moves on an index vector and
+    // apply the result as at most max_row-min_row-1 integer row swaps.
     const size_t niter = 4 * (size_t)(max_row - min_row);
+    const int m        = max_row - min_row;
+    std::vector<int> cur(m);
+    for (int i = 0; i < m; i++)
+      cur[i] = i;
     for (size_t i = 0; i < niter; ++i)
     {
-      size_t a = below(max_row - min_row - 1) + min_row, b = a;
+      size_t a = below(max_row - min_row - 1), b = a;
       while (b == a)
-        b = below(max_row - min_row - 1) + min_row;
-      move_row((int)b, (int)a);
+        b = below(max_row - min_row - 1);
+      const int t = cur[b];  // move_row(b, a): row b lands at a, rows between shift by one
+      cur.erase(cur.begin() + b);
+      cur.insert(cur.begin() + a, t);
+    }
+    {
+      std::vector<int> at(m), where(m);  // at[p] = original row now at position p, where[o] = position of row o
+      for (int i = 0; i < m; i++)
+        at[i] = where[i] = i;
+      for (int p = 0; p < m; p++)
+      {
+        const int q = where[cur[p]];
+        if (q != p)
+        {
+          row_swap(min_row + p, min_row + q);
+          const int op_ = at[p], oq = at[q];
+          at[p] = oq, at[q] = op_;
+          where[oq] = p, where[op_] = q;
+        }
+      }
     }
     for (long a = min_row; a < max_row - 2; ++a)
       for (long i = 0; i < density; i++)
@@ -304,7 +336,12 @@ public:
         rerandomize_block(kappa + 1, kappa + block_size, par.rerandomization_density);
       svp_preprocessing(kappa, block_size, par);
 
-      GCK(b200gso_get_block(g, 0, kappa, block_size, mut.data(), rmant.data(), rexpo.data()));
+      {
+        const double tg = now_s();
+        GCK(b200gso_get_block(g, 0, kappa, block_size, mut.data(), rmant.data(), rexpo.data()));
+        st->sec_get += now_s() - tg;
+        st->get_calls++;
+      }
       long max_dist_expo = rexpo[0];
       double max_dist    = rmant[0] * delta();
       double log_det     = 0;  // get_root_det / get_log_det, gso_interface.cpp:220-242

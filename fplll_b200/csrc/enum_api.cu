@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <mutex>
 #include <string>
@@ -45,7 +46,8 @@ thread_local std::string g_err;
 
 constexpr int SOL_CAP    = 4096;
 constexpr int THREADS    = 128;
-constexpr int MIN_ROOTS  = 2048;     // host breadth phase: grow T until at least this many roots ...
+constexpr int MIN_ROOTS  = 256;      // host breadth phase: grow T until at least this many roots (the device multiplies
+                                    // them by work splitting, a round costs one grid barrier) ...
 constexpr int MAX_ROOTS  = 1 << 18;  // ... but never beyond this
 constexpr unsigned TASK_CAP = 1u << 21;  // device task queue capacity (tasks of all rounds)
 
@@ -67,16 +69,13 @@ struct TaskHdr
 
 struct EnumArgs
 {
-  int d;
+  int d, dstride;              // dim; task prefix row stride (d rounded up to a multiple of 4 ints)
   const double *mut, *rdiag, *prun;
-  const TaskHdr *hdr;          // this round's tasks  [0, end)
-  const int *tx;               // [end * d] coefficients by absolute level (entries > lvl are meaningful)
-  TaskHdr *hdr_out;            // next round's tasks (the other half of the double-buffered queue), [TASK_CAP]
-  int *tx_out;
-  unsigned end;                // number of tasks this round
-  unsigned *ticket;            // next unclaimed task of the round (starts at 0)
-  unsigned *tail;              // append position in the out queue (starts at 0)
-  unsigned budget;             // nodes a walker may visit before it must split
+  TaskHdr *hdrq[2];            // double-buffered task queue: round r reads half r&1, appends to the other half
+  int *txq[2];                 // [TASK_CAP * dstride] coefficients by absolute level (entries > lvl are meaningful)
+  unsigned n_first;            // number of tasks of round 0 (the host's subtree roots, in half 0)
+  unsigned *ctr;               // device counters: [0] ticket, [1] append position, [2] tasks of the current round
+  unsigned budget0, budget_mul;  // nodes a walker may visit before it must split: budget0 * mul^round (capped)
   unsigned long long *A_bits;  // [0] radius (bit pattern of a positive double), [1] best-so-far in fixed-radius mode
   unsigned long long *nodes;   // [d]
   unsigned long long *leaves;
@@ -97,9 +96,14 @@ __device__ inline double next_sibling(double x, double c, double pdk)
 
 // ------------------------------------------------------------------------------------------------------------
 // device depth phase
+// Persistent cooperative kernel: ALL rounds of one enumeration run inside one launch, separated by grid-wide barriers
+// (a round = every walker works off the current half of the task queue, walkers that split or yield append to the other
+// half).  One launch per Enumeration::enumerate call instead of one launch + host synchronisation per round.
 template <int ML>
 __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
 {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sm[];
   const int d = a.d;
   double *s_mut = sm, *s_r = sm + (size_t)d * d, *s_p = s_r + d;
@@ -119,29 +123,52 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
     cnt[k] = 0;
   unsigned long long my_leaves = 0;
   double A     = __longlong_as_double(*(volatile unsigned long long *)a.A_bits);
+  int steps    = 0;
+  unsigned end = a.n_first, budget = a.budget0;
+
+  for (unsigned rno = 0;; ++rno)
+  {
+  const TaskHdr *hdr_in = a.hdrq[rno & 1];
+  const int *tx_in      = a.txq[rno & 1];
+  TaskHdr *hdr_out      = a.hdrq[(rno + 1) & 1];
+  int *tx_out           = a.txq[(rno + 1) & 1];
+  unsigned *ticket = a.ctr, *tail = a.ctr + 1;
   int k        = -2;  // -2: idle (needs a task)
   int top      = 0;   // highest level this walker still owns
   unsigned n   = 0;   // nodes since the last split
-  int steps    = 0;
-
+  unsigned next_check = 64;
   for (;;)
   {
     if (k == -2)
     {
-      const unsigned t = atomicAdd(a.ticket, 1u);
-      if (t >= a.end)
+      const unsigned t = atomicAdd(ticket, 1u);
+      if (t >= end)
         break;
-      const TaskHdr h = a.hdr[t];
-      const int *tx   = a.tx + (size_t)t * d;
+      const TaskHdr h = hdr_in[t];
+      const int4 *tx4 = (const int4 *)(tx_in + (size_t)t * a.dstride);
       A               = __longlong_as_double(*(volatile unsigned long long *)a.A_bits);
       top = k = h.lvl;
-#pragma unroll 1
-      for (int j = k + 1; j < d; j++)
-        x[j] = (double)tx[j];
+      // prefix x[lvl+1 .. d-1]: 128-bit loads, 4 in flight (a walker that starts a task stalls its whole warp, so
+      // this must cost one memory latency, not d of them)
+#pragma unroll 4
+      for (int j4 = (k + 1) >> 2; j4 < (a.dstride >> 2); j4++)
+      {
+        const int4 q = tx4[j4];
+        const int j  = 4 * j4;
+        if (j > k && j < d)
+          x[j] = (double)q.x;
+        if (j + 1 > k && j + 1 < d)
+          x[j + 1] = (double)q.y;
+        if (j + 2 > k && j + 2 < d)
+          x[j + 2] = (double)q.z;
+        if (j + 3 > k && j + 3 < d)
+          x[j + 3] = (double)q.w;
+      }
       pd[k]  = h.pd;
       cen[k] = h.cen;
       x[k]   = h.xs;
       n      = 0;
+      next_check = 64;
     }
 
     // ---- one step of enumerate_loop (enumerate_base.cpp:193-254) ----
@@ -181,9 +208,10 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
         --k;
         // centre: the reference's chain ((0 - x[d-1] mu) - x[d-2] mu) - ... - x[k+1] mu, descending j
         double nc = 0.0;
-#pragma unroll 1
+        const double *mrow = s_mut + (size_t)k * d;
+#pragma unroll 4
         for (int j = d - 1; j > k; --j)
-          nc = __dsub_rn(nc, __dmul_rn(x[j], s_mut[(size_t)k * d + j]));
+          nc = __dsub_rn(nc, __dmul_rn(x[j], mrow[j]));
         cen[k] = nc;
         pd[k]  = newdist;
         x[k]   = round(nc);
@@ -198,36 +226,85 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
       else
         x[k] = next_sibling(x[k], cen[k], pd[k]);
     }
-    else if (n >= a.budget && k < top)
+    else if (n >= next_check)
     {
-      // budget used up: donate the unvisited siblings of every ancestor level (top .. k+1) and keep only the
-      // current node's subtree (levels <= k)
-      int jj = top;
-      for (; jj > k; --jj)
+      // Work split (we are at a just-created node: level k holds its first, not yet tested, candidate x[k]).
+      //  * the round still has unclaimed tasks: a walker that used up its budget donates the unvisited siblings of
+      //    its two top-most ancestor levels (the biggest chunks) and goes on;
+      //  * the round has run dry (idle lanes are waiting): after only 64 more nodes the walker YIELDS — every
+      //    ancestor's remaining siblings plus its current position become tasks of the next round — so the tail of
+      //    a round is bounded by ~64 nodes instead of by the largest subtree.
+      const bool dry = (*(volatile unsigned *)ticket >= end);
+      next_check     = n + 64;
+      if (dry || n >= budget)
       {
-        // siblings come in order of increasing distance from the centre: if the next one is already outside the
-        // bound there is nothing left at this level
-        const double nx = next_sibling(x[jj], cen[jj], pd[jj]);
-        const double al = __dsub_rn(nx, cen[jj]);
-        const double nd = __dadd_rn(pd[jj], __dmul_rn(__dmul_rn(al, al), s_r[jj]));
-        if (!(nd <= __dmul_rn(s_p[jj], A)))
-          continue;
-        const unsigned slot = atomicAdd(a.tail, 1u);
-        if (slot >= TASK_CAP)
-          break;  // queue full: keep levels <= jj ourselves
-        TaskHdr h;
-        h.pd = pd[jj], h.cen = cen[jj], h.xs = nx, h.lvl = jj, h.pad = 0;
-        a.hdr_out[slot] = h;
-        int *tx         = a.tx_out + (size_t)slot * d;
-#pragma unroll 1
-        for (int j = jj + 1; j < d; j++)
-          tx[j] = (int)x[j];
+        int jj = top, given = 0;
+        bool full = false;
+        for (; jj > k && (dry || given < 2); --jj)
+        {
+          // siblings come in order of increasing distance from the centre: if the next one is already outside the
+          // bound there is nothing left at this level
+          const double nx = next_sibling(x[jj], cen[jj], pd[jj]);
+          const double al = __dsub_rn(nx, cen[jj]);
+          const double nd = __dadd_rn(pd[jj], __dmul_rn(__dmul_rn(al, al), s_r[jj]));
+          if (!(nd <= __dmul_rn(s_p[jj], A)))
+            continue;
+          const unsigned slot = atomicAdd(tail, 1u);
+          if (slot >= TASK_CAP)
+          {
+            full = true;
+            break;  // queue full: keep levels <= jj ourselves
+          }
+          TaskHdr h;
+          h.pd = pd[jj], h.cen = cen[jj], h.xs = nx, h.lvl = jj, h.pad = 0;
+          hdr_out[slot] = h;
+          int *tx       = tx_out + (size_t)slot * a.dstride;
+#pragma unroll 4
+          for (int j = jj + 1; j < d; j++)
+            tx[j] = (int)x[j];
+          given++;
+        }
+        top = jj;  // levels above jj are donated or exhausted; the walker keeps the siblings of levels <= jj
+        if (dry && !full && top == k)
+        {
+          const unsigned slot = atomicAdd(tail, 1u);
+          if (slot < TASK_CAP)
+          {
+            TaskHdr h;
+            h.pd = pd[k], h.cen = cen[k], h.xs = x[k], h.lvl = k, h.pad = 0;
+            hdr_out[slot] = h;
+            int *tx       = tx_out + (size_t)slot * a.dstride;
+#pragma unroll 4
+            for (int j = k + 1; j < d; j++)
+              tx[j] = (int)x[j];
+            k = -2;  // yielded: this walker is idle (and the round is dry, so it will leave the loop)
+          }
+        }
+        n          = 0;
+        next_check = 64;
       }
-      top = jj;
-      n   = 0;
     }
     if (((++steps) & 63) == 0 && !a.fixed_radius)
       A = __longlong_as_double(*(volatile unsigned long long *)a.A_bits);
+  }
+  // ---- end of round: everybody has left the walker loop; publish the next round's task count ----
+  __threadfence();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const unsigned produced = *(volatile unsigned *)tail;
+    a.ctr[2] = produced < TASK_CAP ? produced : TASK_CAP;
+    a.ctr[0] = 0;
+    a.ctr[1] = 0;
+    a.ctr[3] = rno + 1;
+    __threadfence();
+  }
+  grid.sync();
+  end = *(volatile unsigned *)(a.ctr + 2);
+  if (end == 0)
+    break;
+  const unsigned long long nb = (unsigned long long)budget * a.budget_mul;
+  budget = nb > 16384ull ? 16384u : (unsigned)nb;
   }
 #pragma unroll 1
   for (int kk = 0; kk < d; kk++)
@@ -453,6 +530,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
 
   const auto t_host = std::chrono::steady_clock::now();
   // ---- device depth phase ----
+  const int dstride  = (d + 3) & ~3;
   const size_t cfg_n = (size_t)d * d + 2 * d;
   std::vector<double> cfg(cfg_n);
   std::copy(mut, mut + (size_t)d * d, cfg.begin());
@@ -460,7 +538,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
   std::copy(prun.begin(), prun.end(), cfg.begin() + (size_t)d * d + d);
   // this shard: sorted position g with g % shard_world == shard_rank; among those, device q takes every ndev-th
   std::vector<DevCtx *> ctxs(ndev);
-  std::vector<unsigned> head(ndev, 0), tail(ndev, 0);
+  std::vector<unsigned> tail(ndev, 0);
   for (int q = 0; q < ndev; q++)
   {
     DevCtx *c;
@@ -470,7 +548,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
     ctxs[q] = c;
     CKE(cudaSetDevice(c->device));
     rc = ensure(&c->d_cfg, &c->cfg_cap, cfg_n);
-    rc |= ensure(&c->d_tx, &c->tx_cap, (size_t)2 * TASK_CAP * d);
+    rc |= ensure(&c->d_tx, &c->tx_cap, (size_t)2 * TASK_CAP * dstride);
     if (rc)
       return rc;
     std::vector<TaskHdr> hdr;
@@ -487,7 +565,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
       h.cen = nc, h.xs = std::round(nc);
       hdr.push_back(h);
       const size_t o = tx.size();
-      tx.resize(o + d, 0);
+      tx.resize(o + dstride, 0);
       for (int t = 0; t < T; t++)
         tx[o + L + t] = rx[t];
     }
@@ -506,63 +584,42 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
     CKE(cudaStreamSynchronize(c->stream));  // hdr/tx are stack vectors
     CKE(cudaEventRecord(c->e0, c->stream));
   }
-  // rounds: every device works through its queue segment [head, tail); walkers that exhaust their node budget append
-  // the unvisited parts as new tasks, which form the next round's segment.  The budget grows geometrically: small
-  // first rounds multiply the parallelism quickly, later rounds amortise the launch.
+  // One cooperative launch per device runs every round of the enumeration (k_enum): walkers that exhaust their node
+  // budget, or notice that the round has run dry, append the unvisited parts of their subtree as tasks of the next
+  // round.  The budget grows geometrically: short first rounds multiply the parallelism, later rounds amortise the
+  // grid barrier.
   static const unsigned budget0 = getenv("B200_ENUM_BUDGET0") ? atoi(getenv("B200_ENUM_BUDGET0")) : 64;
   static const unsigned budget_mul = getenv("B200_ENUM_BUDGET_MUL") ? atoi(getenv("B200_ENUM_BUDGET_MUL")) : 4;
-  unsigned budget = budget0;
-  int rounds      = 0;
+  static const int bpsm = getenv("B200_ENUM_BLOCKS_PER_SM") ? atoi(getenv("B200_ENUM_BLOCKS_PER_SM")) : 4;
   const size_t smem = cfg_n * sizeof(double);
-  for (;;)
+  for (int q = 0; q < ndev; q++)
   {
-    bool any = false;
-    for (int q = 0; q < ndev; q++)
+    if (tail[q] == 0)
+      continue;
+    DevCtx *c = ctxs[q];
+    CKE(cudaSetDevice(c->device));
+    EnumArgs a;
+    a.d = d, a.dstride = dstride, a.mut = c->d_cfg, a.rdiag = c->d_cfg + (size_t)d * d, a.prun = a.rdiag + d;
+    a.hdrq[0] = c->d_hdr, a.hdrq[1] = c->d_hdr + TASK_CAP;
+    a.txq[0] = c->d_tx, a.txq[1] = c->d_tx + (size_t)TASK_CAP * dstride;
+    a.n_first = tail[q];
+    a.ctr = (unsigned *)(c->d_words + 4), a.sol_count = (unsigned *)(c->d_words + 3) + 1;
+    a.budget0 = budget0, a.budget_mul = budget_mul;
+    a.A_bits = c->d_words, a.leaves = c->d_words + 2, a.nodes = c->d_nodes, a.sols = c->d_sols;
+    a.fixed_radius = fixed ? 1 : 0;
+    int occ = 0;
+    const void *fn = d <= 64 ? (const void *)k_enum<64> : (const void *)k_enum<160>;
+    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, THREADS, smem));
+    if (occ < 1)
     {
-      if (tail[q] == 0)
-        continue;
-      any       = true;
-      DevCtx *c = ctxs[q];
-      CKE(cudaSetDevice(c->device));
-      const unsigned zero = 0;
-      // ticket and out-tail restart at 0 every round; sol_count (the word's high half) is cumulative
-      CKE(cudaMemcpyAsync((unsigned *)(c->d_words + 3), &zero, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-      CKE(cudaMemcpyAsync((unsigned *)(c->d_words + 4), &zero, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-      const size_t in = (size_t)(rounds & 1) * TASK_CAP, out = (size_t)((rounds + 1) & 1) * TASK_CAP;
-      EnumArgs a;
-      a.d = d, a.mut = c->d_cfg, a.rdiag = c->d_cfg + (size_t)d * d, a.prun = a.rdiag + d;
-      a.hdr = c->d_hdr + in, a.tx = c->d_tx + in * d, a.hdr_out = c->d_hdr + out, a.tx_out = c->d_tx + out * d;
-      a.end = tail[q];
-      a.ticket = (unsigned *)(c->d_words + 3), a.sol_count = (unsigned *)(c->d_words + 3) + 1;
-      a.tail = (unsigned *)(c->d_words + 4), a.budget = budget;
-      a.A_bits = c->d_words, a.leaves = c->d_words + 2, a.nodes = c->d_nodes, a.sols = c->d_sols;
-      a.fixed_radius = fixed ? 1 : 0;
-      const size_t nt  = tail[q];
-      // resident walkers per SM: each keeps ~24 B x d of stacks in local memory; 2 CTAs x 128 walkers keep the whole
-      // working set in L1/L2 (4+ CTAs/SM spill the stacks to DRAM and run 5x slower)
-      static const int bpsm = getenv("B200_ENUM_BLOCKS_PER_SM") ? atoi(getenv("B200_ENUM_BLOCKS_PER_SM")) : 2;
-      const int blocks = (int)std::max<size_t>(1, std::min<size_t>((nt + THREADS - 1) / THREADS, (size_t)c->sms * bpsm));
-      if (d <= 64)
-        k_enum<64><<<blocks, THREADS, smem, c->stream>>>(a);
-      else
-        k_enum<160><<<blocks, THREADS, smem, c->stream>>>(a);
-      CKE(cudaMemcpyAsync(c->h_words, c->d_words, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      g_err = "b200enum_run: kernel does not fit on an SM";
+      return B200ENUM_ECUDA;
     }
-    if (!any)
-      break;
-    for (int q = 0; q < ndev; q++)
-    {
-      if (tail[q] == 0)
-        continue;
-      DevCtx *c = ctxs[q];
-      CKE(cudaSetDevice(c->device));
-      CKE(cudaStreamSynchronize(c->stream));
-      CKE(cudaGetLastError());
-      tail[q] = std::min<unsigned>(*(unsigned *)(c->h_words + 4), TASK_CAP);
-    }
-    budget = std::min<unsigned>(budget * budget_mul, 16384);
-    rounds++;
+    const int blocks = c->sms * std::min(occ, bpsm);  // every CTA must be resident (grid-wide barrier)
+    void *params[]   = {(void *)&a};
+    CKE(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(THREADS), params, smem, c->stream));
   }
+  int rounds = 0;
   std::vector<uint64_t> tot(d, 0);
   uint64_t host_nodes = 0, dev_nodes = 0, leaves = 0;
   if (shard_rank == 0)
@@ -599,6 +656,7 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
       dev_nodes += c->h_nodes[k];
     }
     leaves += c->h_words[2];
+    rounds = std::max(rounds, (int)((unsigned *)(c->h_words + 4))[3]);
     if (nsol > SOL_CAP)
       overflow = true;
     for (unsigned s = 0; s < std::min<unsigned>(nsol, SOL_CAP); s++)

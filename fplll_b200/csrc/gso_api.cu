@@ -6,6 +6,7 @@
 // sweep loops) is what hides DRAM latency, not shared-memory tiling.  There is no CPU fallback anywhere.
 #include "../../include/b200gso.h"
 #include "gso_lll.cuh"
+#include "gso_tma.cuh"
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -109,6 +110,41 @@ __global__ void k_discover_all(Batch S)
     return;
   while (v.meta[M_NKR] < v.d)
     warp_discover_row(v, lane);
+}
+
+// TMA-staged variant (gso_tma.cuh): per warp  vb | rrow | murow | ring[TMA_STAGES][512] | mbarriers
+__host__ __device__ inline size_t tma_warp_doubles(int d, int n)
+{
+  return ((WarpSmem::doubles(d, n, false) + 15) & ~(size_t)15) + (size_t)TMA_STAGES * TMA_CHUNK_DBL + TMA_STAGES;
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) k_update_row_tma(Batch S, int i, int last_j, int *ok)
+{
+  extern __shared__ __align__(128) double smem_t[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = blockIdx.x * (blockDim.x >> 5) + w;
+  if (l >= S.B)
+    return;
+  double *base = smem_t + (size_t)w * tma_warp_doubles(S.d, S.n);
+  WarpSmem s;
+  s.carve(base, S.d, S.n, false);
+  double *ring = base + ((WarpSmem::doubles(S.d, S.n, false) + 15) & ~(size_t)15);
+  unsigned long long *bars = (unsigned long long *)(ring + (size_t)TMA_STAGES * TMA_CHUNK_DBL);
+  View v = S.view(l);
+  if (i >= v.meta[M_NKR])
+    warp_discover_row(v, lane);
+  // fast path only for a full recompute: nothing of row i valid, whole Gram row invalid
+  int notnan = 0;
+  const double *gfrow = v.gf + tri_off(i);
+  for (int j = lane; j <= last_j; j += 32)
+    notnan |= (gfrow[j] == gfrow[j]);
+  notnan = __any_sync(FULL, notnan);
+  bool r;
+  if (v.valid[i] <= 0 && !notnan)
+    r = warp_update_gso_row_tma(v, i, last_j, s, ring, bars, lane);
+  else
+    r = warp_update_gso_row(v, i, last_j, s, lane);
+  if (ok && lane == 0)
+    ok[l] = r ? 1 : 0;
 }
 
 template <int MINB>
@@ -415,6 +451,19 @@ static int grid_warps(const b200gso *h) { return (h->S.B + WARPS_PER_CTA - 1) / 
 static void launch_update_row(b200gso *h, int i, int last_j)
 {
   const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
+  static const int use_tma = getenv("B200_UPD_TMA") ? atoi(getenv("B200_UPD_TMA")) : 0;
+  if (use_tma)
+  {
+    const size_t sm = (size_t)WARPS_PER_CTA * tma_warp_doubles(h->S.d, h->S.n) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+      cudaFuncSetAttribute((const void *)k_update_row_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    k_update_row_tma<<<g, t, sm, h->stream>>>(h->S, i, last_j, h->d_ok);
+    return;
+  }
   switch (upd_variant())
   {
   case 5: k_update_row<5><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;

@@ -402,6 +402,52 @@ __device__ inline int size_nz_warp(const int64_t *row, int n, int lane)
   return last;
 }
 
+// Rotate the sequence e(lo), ..., e(hi) by one position (right: e(hi) -> lo, the rest shift up; left: e(lo) -> hi).
+// `at(i)` returns a reference to element i.  Elements are moved in chunks of 8 held in registers so that 8 loads are in
+// flight at a time: written as a one-by-one shift, every load would wait for the previous store (same array) and a
+// rotation over D rows would cost D dependent memory round trips.
+template <class T, class At> __device__ inline void rotate_seq(At at, int lo, int hi, bool right)
+{
+  if (hi <= lo)
+    return;
+  if (right)
+  {
+    const T t = at(hi);
+    int i     = hi;
+    for (; i - 8 >= lo; i -= 8)
+    {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = at(i - 1 - u);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        at(i - u) = v[u];
+    }
+    for (; i > lo; --i)
+      at(i) = at(i - 1);
+    at(lo) = t;
+  }
+  else
+  {
+    const T t = at(lo);
+    int i     = lo;
+    for (; i + 8 <= hi; i += 8)
+    {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = at(i + 1 + u);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        at(i + u) = v[u];
+    }
+    for (; i < hi; ++i)
+      at(i) = at(i + 1);
+    at(hi) = t;
+  }
+}
+
 // move_row(old_r, new_r), gso.cpp:289-366 (float Gram, no transforms).  Rotations of mu, r, b, bf, row_expo,
 // gso_valid_cols are done column-by-column (each lane carries one column through the rotated rows, no scratch);
 // only the entries that can still be valid after the call (columns < min(old,new)) are moved
@@ -417,69 +463,16 @@ __device__ inline void warp_move_row(const View &v, int old_r, int new_r, int la
     v.valid[i] = min(v.valid[i], lo);
   lower_clean(v, lo, lane);
   __syncwarp();
-  // mu (columns k < lo) — panel layout
+  // mu and r (columns k < lo), b and bf rows (all n columns): one column per lane, rows rotated in register chunks
   for (int k = lane; k < lo; k += 32)
   {
-    if (right)
-    {
-      double t = v.mu[mu_off(hi, k)];
-      for (int i = hi; i > lo; i--)
-        v.mu[mu_off(i, k)] = v.mu[mu_off(i - 1, k)];
-      v.mu[mu_off(lo, k)] = t;
-    }
-    else
-    {
-      double t = v.mu[mu_off(lo, k)];
-      for (int i = lo; i < hi; i++)
-        v.mu[mu_off(i, k)] = v.mu[mu_off(i + 1, k)];
-      v.mu[mu_off(hi, k)] = t;
-    }
+    rotate_seq<double>([&](int i) -> double & { return v.mu[mu_off(i, k)]; }, lo, hi, right);
+    rotate_seq<double>([&](int i) -> double & { return v.r[tri_off(i) + k]; }, lo, hi, right);
   }
-  // r (columns k < lo)
-  for (int k = lane; k < lo; k += 32)
-  {
-    if (right)
-    {
-      double t = v.r[tri_off(hi) + k];
-      for (int i = hi; i > lo; i--)
-        v.r[tri_off(i) + k] = v.r[tri_off(i - 1) + k];
-      v.r[tri_off(lo) + k] = t;
-    }
-    else
-    {
-      double t = v.r[tri_off(lo) + k];
-      for (int i = lo; i < hi; i++)
-        v.r[tri_off(i) + k] = v.r[tri_off(i + 1) + k];
-      v.r[tri_off(hi) + k] = t;
-    }
-  }
-  // b and bf rows (all n columns)
   for (int c = lane; c < v.n; c += 32)
   {
-    if (right)
-    {
-      int64_t t = v.b[(size_t)hi * v.ldb + c];
-      double tf = v.bf[bf_off(hi, c, v.n)];
-      for (int i = hi; i > lo; i--)
-      {
-        v.b[(size_t)i * v.ldb + c] = v.b[(size_t)(i - 1) * v.ldb + c];
-        v.bf[bf_off(i, c, v.n)]    = v.bf[bf_off(i - 1, c, v.n)];
-      }
-      v.b[(size_t)lo * v.ldb + c] = t;
-      v.bf[bf_off(lo, c, v.n)]    = tf;
-    }
-    else
-    {
-      int64_t t = v.b[(size_t)lo * v.ldb + c];
-      double tf = v.bf[bf_off(lo, c, v.n)];
-      for (int i = lo; i < hi; i++)
-      {
-        v.b[(size_t)i * v.ldb + c] = v.b[(size_t)(i + 1) * v.ldb + c];
-        v.bf[bf_off(i, c, v.n)]    = v.bf[bf_off(i + 1, c, v.n)];
-      }
-      v.b[(size_t)hi * v.ldb + c] = t;
-      v.bf[bf_off(hi, c, v.n)]    = tf;
-    }
+    rotate_seq<int64_t>([&](int i) -> int64_t & { return v.b[(size_t)i * v.ldb + c]; }, lo, hi, right);
+    rotate_seq<double>([&](int i) -> double & { return v.bf[bf_off(i, c, v.n)]; }, lo, hi, right);
   }
   // gf: new(i,j) = old_sym(s(i), s(j)) on the known rows; rotate_gram_left only when old_r < nkr-1 and up to
   // min(new_r, nkr-1) (gso.cpp:338-341).  Rows below the rotated range only permute their columns [lo, ghi] (done in
@@ -491,20 +484,7 @@ __device__ inline void warp_move_row(const View &v, int old_r, int new_r, int la
       for (int i = ghi + 1 + lane; i < nkr; i += 32)
       {
         double *row = v.gf + tri_off(i);
-        if (right)
-        {
-          const double t = row[ghi];
-          for (int j = ghi; j > lo; --j)
-            row[j] = row[j - 1];
-          row[lo] = t;
-        }
-        else
-        {
-          const double t = row[lo];
-          for (int j = lo; j < ghi; ++j)
-            row[j] = row[j + 1];
-          row[ghi] = t;
-        }
+        rotate_seq<double>([&](int j) -> double & { return row[j]; }, lo, ghi, right);
       }
       const size_t beg = tri_off(lo), end = tri_off(ghi + 1);
       for (size_t t = beg + lane; t < end; t += 32)
@@ -525,42 +505,13 @@ __device__ inline void warp_move_row(const View &v, int old_r, int new_r, int la
     }
   }
   __syncwarp();
-  // row_expo, gso_valid_cols (and init_row_size when the row leaves the known set): lane 0, tiny
+  // row_expo, gso_valid_cols (and init_row_size when the row leaves the known set): three lanes, one array each
   if (lane == 0)
-  {
-    if (right)
-    {
-      int tv = v.valid[hi], te = v.row_expo[hi];
-      for (int i = hi; i > lo; i--)
-      {
-        v.valid[i]    = v.valid[i - 1];
-        v.row_expo[i] = v.row_expo[i - 1];
-      }
-      v.valid[lo] = tv;
-      if (v.row_expo_en)
-        v.row_expo[lo] = te;
-      else
-        v.row_expo[lo] = te;
-    }
-    else
-    {
-      int tv = v.valid[lo], te = v.row_expo[lo];
-      for (int i = lo; i < hi; i++)
-      {
-        v.valid[i]    = v.valid[i + 1];
-        v.row_expo[i] = v.row_expo[i + 1];
-      }
-      v.valid[hi]    = tv;
-      v.row_expo[hi] = te;
-      if (new_r >= nkr)
-      {
-        int ti = v.irs[lo];
-        for (int i = lo; i < hi; i++)
-          v.irs[i] = v.irs[i + 1];
-        v.irs[hi] = ti;
-      }
-    }
-  }
+    rotate_seq<int>([&](int i) -> int & { return v.valid[i]; }, lo, hi, right);
+  else if (lane == 1)
+    rotate_seq<int>([&](int i) -> int & { return v.row_expo[i]; }, lo, hi, right);
+  else if (lane == 2 && !right && new_r >= nkr)
+    rotate_seq<int>([&](int i) -> int & { return v.irs[i]; }, lo, hi, false);
   __syncwarp();
   if (!right && new_r >= nkr && old_r < nkr)
   {

@@ -41,6 +41,12 @@ def _lib():
         L.b200gso_get_state.argtypes = [vp, dp, dp, dp, dp, i64p, ip, ip, ip]
         L.b200gso_get_mu_r_row.argtypes = [vp, i, dp, dp, ip]
         L.b200gso_lll.argtypes = [vp, C.c_double, C.c_double, ip, lp]
+        L.b200gso_lll_range.argtypes = [vp, C.c_double, C.c_double, i, i, i, i, ip, lp]
+        L.b200gso_size_reduction.argtypes = [vp, C.c_double, i, i, i, ip]
+        L.b200gso_negate_row_of_b.argtypes = [vp, i]
+        L.b200gso_get_block.argtypes = [vp, i, i, i, dp, dp, lp]
+        L.b200gso_get_r_diag.argtypes = [vp, i, i, i, dp, lp]
+        L.b200gso_apply_ops.argtypes = [vp, C.c_void_p, i]
         L.b200gso_time_update_row.argtypes = [vp, i, i, i, _P(C.c_float), _P(C.c_float)]
         L.b200gso_sync.argtypes = [vp]
         L.b200gso_resident_lattices.argtypes = [vp]

@@ -1,7 +1,7 @@
 import sys, time, os, subprocess, numpy as np
 sys.path.insert(0, "tests")
 import helpers as H
-from fplll_b200 import enum as en
+from fplll_b200 import enumeration as en
 from test_enum_oracle import gso_block
 names = sys.argv[1:]
 for name in names:

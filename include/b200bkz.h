@@ -57,6 +57,8 @@ typedef struct
   uint64_t enum_nodes;
   long enum_calls, lll_calls, sizered_calls;
   double sec_total, sec_enum, sec_lll, sec_other;
+  double sec_ops, sec_get; /* inside sec_other: op-list launches (post-processing, rerandomisation), block read-backs */
+  long op_calls, ops_total, get_calls;
   double r00_before, r00_after; /* squared norm of b_0 */
   double slope_before, slope_after;
 } b200bkz_stats;

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def en():
-    from fplll_b200 import enum
+    from fplll_b200 import enumeration as enum
     return enum
 
 
