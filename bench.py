@@ -146,6 +146,69 @@ def enum_extras(local):
     return out
 
 
+def hh_extras(local):
+    """Householder update_R(i) (householder.cpp:151-184) at config #3's shape d = n = 400, i = 399, batched; algorithmic
+    bytes per lattice 8*[T(i) + 2n], T(i) = i*n - i(i-1)/2 (V rows streamed once, R_i read+written; history off)."""
+    import numpy as np
+    out = {}
+    try:
+        from fplll_b200.householder import MatHouseholder
+        d = n = 400
+        i = d - 1
+        B = 2368
+        rng = np.random.default_rng(7)
+        b = rng.integers(-(1 << 20), 1 << 20, size=(1, d, n), dtype=np.int64)
+        m = MatHouseholder(np.broadcast_to(b, (B, d, n)), 5, device=local, keep_history=False)
+        m.refresh_R_bf(i)
+        m.time_update_R(i, 2)
+        ms = m.time_update_R(i, 5)
+        T = i * n - i * (i - 1) // 2
+        per = 8 * (T + 2 * n)
+        peak, _ = peaks()
+        out = {"workload": "batched update_R(399, false) on %d lattices of d=n=400 (V zero-filled: timing only)" % B,
+               "algorithmic_bytes_per_lattice": per, "ms_per_launch": ms, "GBps": B * per / (ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": B * per / (ms * 1e-3) / 1e9 / peak}
+        m.close()
+    except Exception as ex:
+        out["error"] = str(ex)[:300]
+    return out
+
+
+def bkz_extras(local):
+    """The BKZ half of the BASELINE metric: wall-seconds of ONE tour of BKZ-60 (strategies/default.json table, fp64,
+    BKZ_NO_LLL | BKZ_MAX_LOOPS=1) on the wrapper-LLL-reduced latticegen r 200 2000 basis (tests/golden), device GSO/LLL +
+    device enumeration, next to the reference's bkz_reduction on the same input on the host (1 thread = the CLI default,
+    and all threads through set_threads)."""
+    import numpy as np
+    out = {}
+    try:
+        import fplll_b200 as fb
+        g = np.load(os.path.join(ROOT, "tests", "golden", "r200_lll_update_gso.npz"))
+        b = g["b"].copy()
+        t0 = time.perf_counter()
+        st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
+                                                    max_loops=1, seed=1), devices=[local])
+        out = {"workload": "BKZ-60, 1 tour, default strategies, dim-200 knapsack (LLL-reduced latticegen r 200 2000)",
+               "status": int(st), "wall_seconds": time.perf_counter() - t0, "sec_lll_sizered": stats["sec_lll"],
+               "sec_enum": stats["sec_enum"], "enum_nodes": int(stats["enum_nodes"]), "enum_calls": int(stats["enum_calls"]),
+               "r00_before": stats["r00_before"], "r00_after": stats["r00_after"], "slope_after": stats["slope_after"]}
+        from oracle import oracle as O
+        if O.have_ref():
+            tmp = tempfile.mkdtemp(prefix="bench_bkz_")
+            mat = os.path.join(tmp, "b.txt")
+            O.write_matrix(mat, g["b"])
+            cores = os.cpu_count() or 1
+            ref = {}
+            for th in (1, cores):
+                o = O.run_ref("load %s\nbkz 60 %d 1 default enumlib %d\n" % (mat, 2 | 4, th), timeout=900)
+                tok = dict(t.split("=") for t in o.split("bkz ")[-1].split() if "=" in t)
+                ref["threads_%d" % th] = {"status": int(tok["status"]), "wall_seconds": float(tok["sec"])}
+            out["cpu_reference"] = ref
+    except Exception as ex:
+        out["error"] = str(ex)[:300]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,7 +217,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="lattices per GPU (0 = two full waves of the update kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the enumeration figure")
+    ap.add_argument("--no-extras", action="store_true", help="skip the enumeration / Householder / BKZ figures")
+    ap.add_argument("--no-bkz", action="store_true", help="skip the BKZ-60 tour (about 1.5 min GPU + 1-2 min CPU reference)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,12 +337,17 @@ def main():
                            "algorithmic_bytes_per_lattice": per_lat},
                 "roofline": {"bound": "hbm", "kernel": "k_update_row (update_gso_row, g=1)", "achieved": kern_gbps,
                              "peak": peak, "unit": "GB/s", "frac": kern_gbps / peak, "peak_source": peak_src,
-                             "traffic": None, "ms_per_launch": ms_update},
+                             # dram__bytes_read+write of one launch under `ncu --set full` at this batch size
+                             # (profiles/r1_update_row_ncu_summary.txt, shipped default = the l2f32 capture)
+                             "traffic": 2.990e9 if B == 5920 else None, "ms_per_launch": ms_update},
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s / a.steps * 1e3},
                 "gpu_launches": 2 * a.steps, "clocks": clocks}
         if not a.no_extras and world == 1:
             line["enum"] = enum_extras(local)
+            line["householder"] = hh_extras(local)
+            if not a.no_bkz:
+                line["bkz60"] = bkz_extras(local)
         if not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference()

@@ -36,7 +36,7 @@ _done = False
 
 def _lib():
     global _done
-    L = load("libb200bkz.so")
+    L = load(os.environ.get("B200_BKZ_LIB", "libb200bkz.so"))  # B200_BKZ_LIB: profiling build (see csrc/gso_lll.cuh)
     if not _done:
         L.b200bkz_last_error.restype = C.c_char_p
         L.b200bkz_default_param.argtypes = [_P(_Param), C.c_int]

@@ -87,10 +87,16 @@ public:
   {
     const double t0 = now_s();
     int status      = 0;
-    long stats[4]   = {0, 0, 0, 0};
+    long stats[8]   = {0, 0, 0, 0, 0, 0, 0, 0};
     GCK(b200gso_lll_range(g, lll_delta, 0.51, kmin, kstart, kend, 0, &status, stats));
-    st->sec_lll += now_s() - t0;
+    const double dt = now_s() - t0;
+    st->sec_lll += dt;
     st->lll_calls++;
+#ifdef B200_LLL_PROFILE
+    prof_cyc[0] += stats[4], prof_cyc[1] += stats[5], prof_cyc[2] += stats[6], prof_cyc[3] += stats[7];
+    prof_lll_sec += dt;
+    prof_swaps += stats[0], prof_iters += stats[3];
+#endif
     if (n_swaps)
       *n_swaps = stats[0];
     if (status != 0)
@@ -114,6 +120,9 @@ public:
     st->sec_get += now_s() - t0;
     st->get_calls++;
   }
+  long long prof_cyc[4] = {0, 0, 0, 0};
+  double prof_lll_sec    = 0;
+  long prof_swaps = 0, prof_iters = 0;
   // recorded GSO calls, flushed as one kernel launch (b200gso_apply_ops)
   std::vector<b200gso_op> ops;
   void op(int type, int a, int b, double x = 0.0)
@@ -635,6 +644,12 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
       stats->status = f.status;  // the reference lets this escape as runtime_error; report the status
     }
     stats->sec_total = now_s() - tb;
+#ifdef B200_LLL_PROFILE
+    fprintf(stderr, "LLL profile (lll calls only): %.1f s wall; device cycles update_gso_row %.3g, babai-rest %.3g, "
+                    "lovasz %.3g, move_row+set_r %.3g; swaps %ld, babai iterations %ld\n",
+            drv.prof_lll_sec, (double)drv.prof_cyc[0], (double)drv.prof_cyc[1], (double)drv.prof_cyc[2],
+            (double)drv.prof_cyc[3], drv.prof_swaps, drv.prof_iters);
+#endif
     stats->sec_other = stats->sec_total - stats->sec_enum - stats->sec_lll;
     if (stats->status == 0 || stats->status == B200_RED_BKZ_LOOPS_LIMIT || stats->status == B200_RED_BKZ_TIME_LIMIT)
     {

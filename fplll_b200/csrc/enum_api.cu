@@ -548,7 +548,9 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
     ctxs[q] = c;
     CKE(cudaSetDevice(c->device));
     rc = ensure(&c->d_cfg, &c->cfg_cap, cfg_n);
-    rc |= ensure(&c->d_tx, &c->tx_cap, (size_t)2 * TASK_CAP * dstride);
+    // sized for dim <= 64 up front (BKZ calls with every block size from 2 to beta: growing would re-allocate ~1 GB
+    // a dozen times), re-allocated once if a larger dimension ever shows up
+    rc |= ensure(&c->d_tx, &c->tx_cap, (size_t)2 * TASK_CAP * (dstride <= 64 ? 64 : B200ENUM_MAX_DIM));
     if (rc)
       return rc;
     std::vector<TaskHdr> hdr;

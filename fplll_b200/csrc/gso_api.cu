@@ -8,6 +8,7 @@
 #include "gso_lll.cuh"
 #include "gso_tma.cuh"
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,6 +31,46 @@ thread_local std::string g_err;
     }                                                                                              \
   } while (0)
 
+// The LLL-family kernels (k_lll, k_size_reduction, k_apply_ops) are chains of short dependent steps on ONE lattice per
+// warp; every read of gso_valid_cols / row_expo / init_row_size / n_known_* from global memory is a ~0.5 us round trip
+// on the critical path.  MetaCache stages those arrays in shared memory for the lifetime of the kernel (the View's
+// pointers are simply re-pointed, every device routine keeps working unchanged) and writes them back at the end.
+struct MetaCache
+{
+  int *g_valid, *g_expo, *g_irs, *g_meta;
+  int d;
+  __host__ __device__ static size_t ints(int d) { return 3 * (size_t)((d + 3) & ~3) + M_STRIDE; }
+  __device__ void load(View &v, int *sm, int lane)
+  {
+    d = v.d;
+    const int dp = (d + 3) & ~3;
+    g_valid = v.valid, g_expo = v.row_expo, g_irs = v.irs, g_meta = v.meta;
+    int *s_valid = sm, *s_expo = sm + dp, *s_irs = sm + 2 * dp, *s_meta = sm + 3 * dp;
+    for (int i = lane; i < d; i += 32)
+    {
+      s_valid[i] = g_valid[i];
+      s_expo[i]  = g_expo[i];
+      s_irs[i]   = g_irs[i];
+    }
+    if (lane < M_STRIDE)
+      s_meta[lane] = g_meta[lane];
+    v.valid = s_valid, v.row_expo = s_expo, v.irs = s_irs, v.meta = s_meta;
+    __syncwarp();
+  }
+  __device__ void store(const View &v, int lane)
+  {
+    __syncwarp();
+    for (int i = lane; i < d; i += 32)
+    {
+      g_valid[i] = v.valid[i];
+      g_expo[i]  = v.row_expo[i];
+      g_irs[i]   = v.irs[i];
+    }
+    if (lane < M_STRIDE)
+      g_meta[lane] = v.meta[lane];
+  }
+};
+
 template <bool FULL_SMEM = true>
 __device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *&lov, int &lane)
 {
@@ -38,7 +79,7 @@ __device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *
   lane        = threadIdx.x & 31;
   const int l = blockIdx.x * (blockDim.x >> 5) + w;
   const size_t base = WarpSmem::doubles(S.d, S.n, FULL_SMEM);
-  const size_t per  = base + (FULL_SMEM ? (size_t)((S.d + 2 + 1) & ~1) : 0);
+  const size_t per  = base + (FULL_SMEM ? (size_t)((S.d + 2 + 1) & ~1) + ((MetaCache::ints(S.d) + 1) >> 1) : 0);
   s.carve(smem + (size_t)w * per, S.d, S.n, FULL_SMEM);
   lov = FULL_SMEM ? smem + (size_t)w * per + base : nullptr;
   if (l >= S.B)
@@ -46,6 +87,8 @@ __device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *
   v = S.view(l);
   return true;
 }
+
+__device__ inline int *meta_scratch(const Batch &S, double *lov) { return (int *)(lov + ((S.d + 2 + 1) & ~1)); }
 
 // size_increased(), gso.cpp:368-403: init_row_size, zero-filled bf, update_bf for every row; fresh metadata.
 __global__ void k_init(Batch S)
@@ -312,7 +355,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     return;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   LLLStats st;
+  MetaCache mc;
+  mc.load(v, meta_scratch(S, lov), lane);
   const int r = warp_lll<MAXQ>(v, s, lov, delta, eta, kmin, kstart, kend, sr_start, lane, st);
+  mc.store(v, lane);
   if (lane == 0)
   {
     status[l] = r;
@@ -320,6 +366,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     {
       stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
       stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
+#ifdef B200_LLL_PROFILE
+      // profiling builds (batch 1 only): overwrite final_kappa/zeros/babai_iters slots?  no — append after the batch block
+      long *px = stats + 4 * S.B;
+      px[0] = st.cyc_update, px[1] = st.cyc_babai, px[2] = st.cyc_lovasz, px[3] = st.cyc_move;
+#endif
     }
   }
 }
@@ -336,7 +387,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     return;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   long iters  = 0;
+  MetaCache mc;
+  mc.load(v, meta_scratch(S, lov), lane);
   const int r = warp_size_reduction<MAXQ>(v, s, kmin, kend, sr_start, eta, lane, iters);
+  mc.store(v, lane);
   if (lane == 0)
     status[l] = r;
 }
@@ -349,6 +403,8 @@ __global__ void k_apply_ops(Batch S, const b200gso_op *ops, int n)
   int lane;
   if (!warp_setup(S, v, s, lov, lane))
     return;
+  MetaCache mc;
+  mc.load(v, meta_scratch(S, lov), lane);
   for (int t = 0; t < n; t++)
   {
     const b200gso_op op = ops[t];
@@ -366,6 +422,7 @@ __global__ void k_apply_ops(Batch S, const b200gso_op *ops, int n)
     }
     __syncwarp();
   }
+  mc.store(v, lane);
 }
 
 // MatGSO::negate_row_of_b(i), gso.h:291-297 (integer row only)
@@ -431,6 +488,10 @@ struct b200gso
   int64_t *d_rows;    // batch*n   (upload_row staging)
   double *d_rowbuf;   // 2*batch*d (get_mu_r_row staging)
   int *d_valid_i;     // batch
+  long *d_stats;      // 4*batch (LLL statistics)
+  double *d_blk;      // d*d + 2*d doubles + d longs (get_block / get_r_diag staging)
+  b200gso_op *d_ops;  // op-list staging (grown on demand)
+  size_t ops_cap;
   std::vector<void *> allocs;
 };
 
@@ -548,6 +609,9 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   rc |= dev_alloc(h, &h->d_rows, (size_t)batch * n);
   rc |= dev_alloc(h, &h->d_rowbuf, (size_t)2 * batch * d);
   rc |= dev_alloc(h, &h->d_valid_i, (size_t)batch);
+  rc |= dev_alloc(h, &h->d_stats, (size_t)batch * 4 + 8);
+  rc |= dev_alloc(h, &h->d_blk, (size_t)d * d + 4 * (size_t)d + 16);
+  h->d_ops = nullptr, h->ops_cap = 0;
   if (rc)
   {
     for (void *p : h->allocs)
@@ -556,7 +620,8 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
     return B200GSO_ENOMEM;
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  h->smem_bytes = WARPS_PER_CTA * (WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1)) * sizeof(double);
+  h->smem_bytes = WARPS_PER_CTA * (WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1) + ((MetaCache::ints(d) + 1) >> 1)) *
+                  sizeof(double);
   h->smem_compact = WARPS_PER_CTA * WarpSmem::doubles(d, n, false) * sizeof(double);
   if (h->smem_bytes > 227 * 1024)
   {
@@ -594,6 +659,8 @@ void b200gso_destroy(b200gso_t *h)
   }
   for (void *p : h->allocs)
     cudaFree(p);
+  if (h->d_ops)
+    cudaFree(h->d_ops);
   delete h;
 }
 
@@ -860,9 +927,8 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
     return B200GSO_EINVAL;
   }
   int *d_st     = h->d_ok;
-  long *d_stats = nullptr;
-  if (stats)
-    CK(cudaMallocAsync(&d_stats, sizeof(long) * 4 * S.B, h->stream));
+  long *d_stats = stats ? h->d_stats : nullptr;  // preallocated: stream-ordered allocation would hand its memory back
+                                                 // to the driver at every synchronisation and cost milliseconds
   const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
 #define LLL_LAUNCH(Q)                                                                                          \
   do                                                                                                           \
@@ -882,8 +948,11 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
   CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
   if (stats)
   {
+#ifdef B200_LLL_PROFILE
+    CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * (4 * S.B + 4), cudaMemcpyDeviceToHost, h->stream));
+#else
     CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaFreeAsync(d_stats, h->stream));
+#endif
   }
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -936,11 +1005,16 @@ int b200gso_apply_ops(b200gso_t *h, const b200gso_op *ops, int n)
     }
   }
   CK(cudaSetDevice(h->device));
-  b200gso_op *d_ops = nullptr;
-  CK(cudaMallocAsync(&d_ops, sizeof(b200gso_op) * n, h->stream));
+  if ((size_t)n > h->ops_cap)
+  {
+    if (h->d_ops)
+      cudaFree(h->d_ops);
+    h->ops_cap = std::max<size_t>(1024, (size_t)n * 2);
+    CK(cudaMalloc(&h->d_ops, sizeof(b200gso_op) * h->ops_cap));
+  }
+  b200gso_op *d_ops = h->d_ops;
   CK(cudaMemcpyAsync(d_ops, ops, sizeof(b200gso_op) * n, cudaMemcpyHostToDevice, h->stream));
   k_apply_ops<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, d_ops, n);
-  CK(cudaFreeAsync(d_ops, h->stream));
   CK(cudaStreamSynchronize(h->stream));  // `ops` is caller memory
   CK(cudaGetLastError());
   return 0;
@@ -951,13 +1025,11 @@ int b200gso_get_r_diag(b200gso_t *h, int lattice, int first, int count, double *
   if (!h || lattice < 0 || lattice >= h->S.B || first < 0 || count < 1 || first + count > h->S.d || !r_mant || !r_expo)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  double *t = nullptr;
-  CK(cudaMallocAsync(&t, (size_t)count * (8 + sizeof(long)), h->stream));
-  long *te = (long *)(t + count);
+  double *t = h->d_blk;
+  long *te  = (long *)(t + count);
   k_get_r_diag<<<(count + 127) / 128, 128, 0, h->stream>>>(h->S, lattice, first, count, t, te);
   CK(cudaMemcpyAsync(r_mant, t, (size_t)count * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(r_expo, te, (size_t)count * sizeof(long), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaFreeAsync(t, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;
@@ -969,15 +1041,13 @@ int b200gso_get_block(b200gso_t *h, int lattice, int first, int beta, double *mu
       !r_expo)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  double *t = nullptr;
+  double *t       = h->d_blk;
   const size_t nd = (size_t)beta * beta + beta;
-  CK(cudaMallocAsync(&t, nd * 8 + beta * sizeof(long), h->stream));
-  long *te = (long *)(t + nd);
+  long *te        = (long *)(t + nd);
   k_get_block<<<1, 256, 0, h->stream>>>(h->S, lattice, first, beta, t, t + (size_t)beta * beta, te);
   CK(cudaMemcpyAsync(mut, t, (size_t)beta * beta * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(r_mant, t + (size_t)beta * beta, beta * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(r_expo, te, beta * sizeof(long), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaFreeAsync(t, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;

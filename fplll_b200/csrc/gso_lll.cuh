@@ -15,18 +15,37 @@ constexpr long SIZE_RED_FAILURE_THRESH = 5;                                     
 struct LLLStats
 {
   long n_swaps, final_kappa, zeros, babai_iters;
+  // device-clock breakdown (SM cycles of the owning warp): update_gso_row, rest of babai (scan, back-substitution,
+  // integer row operations, row_op_end), Lovasz test, move_row
+  long long cyc_update, cyc_babai, cyc_lovasz, cyc_move;
 };
+
+#ifdef B200_LLL_PROFILE
+#define LLL_T0() const long long t0_ = clock64()
+#define LLL_ACC(field) (field) += clock64() - t0_
+#else
+#define LLL_T0()
+#define LLL_ACC(field)
+#endif
 
 // LLLReduction::babai(kappa, size_reduction_end, size_reduction_start), lll.cpp:166-224.
 // MAXQ*32 >= d.  Returns RED_SUCCESS or the failing status (warp-uniform).
 template <int MAXQ>
 __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int sr_start, double eta,
-                                 int lane, long &iters)
+                                 int lane, long &iters, long long *cyc_update = nullptr)
 {
   long max_expo = LONG_MAX;
   for (int iter = 0;; iter++)
   {
-    if (!warp_update_gso_row(v, kappa, sr_end - 1, s, lane))
+#ifdef B200_LLL_PROFILE
+    const long long tu_ = clock64();
+#endif
+    const bool upd_ok = warp_update_gso_row(v, kappa, sr_end - 1, s, lane);
+#ifdef B200_LLL_PROFILE
+    if (cyc_update)
+      *cyc_update += clock64() - tu_;
+#endif
+    if (!upd_ok)
       return RED_GSO_FAILURE;
     // gather row kappa of mu (stride-32 in the panel layout) + exponent differences
     const int ek = v.row_expo[kappa];
@@ -60,6 +79,10 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
     }
     iters++;
     __syncwarp();
+    unsigned *xmask = (unsigned *)(s.xs + ((v.d + 1) & ~1));  // per-panel bit masks of the non-zero X_j (padding of xs)
+    if (lane < MAXQ)
+      xmask[lane] = 0;
+    __syncwarp();
     // back-substitution, j descending (lll.cpp:202-214): X_j = rnd_we(babai_mu[j]); babai_mu[k] -= X_j*mu(j,k), k<j
     for (int p = (sr_end - 1) >> 5; p >= (sr_start >> 5); --p)
     {
@@ -71,6 +94,14 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
           val = bm[q];
       const int kcol        = 32 * p + lane;
       const double *tilecol = v.mu + mu_panel_base(p) + (size_t)kcol * 32;  // mu(32p+t, kcol) at [t]
+      unsigned nzmask       = 0;  // rows of this panel with X != 0 (warp-uniform)
+      // this lane's column of the diagonal tile, requested up front: inside the serial t-loop every load would be a
+      // ~0.3 us round trip on the critical path (the device profile showed Babai dominated by exactly that)
+      double tc[32];
+#pragma unroll
+      for (int t = 0; t < 32; t++)
+        tc[t] = (t > lane && 32 * p + t < sr_end) ? tilecol[t] : 0.0;
+#pragma unroll
       for (int t = 31; t >= 0; --t)
       {
         const int j = 32 * p + t;
@@ -81,33 +112,34 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
         const double X  = rnd_we(bj, de);
         if (X == 0.0)
           continue;
+        nzmask |= 1u << t;
         if (lane == 0)
           s.xs[j] = X;
         if (lane < t && kcol >= sr_start)
-          val = __dsub_rn(val, __dmul_rn(X, tilecol[t]));
+          val = __dsub_rn(val, __dmul_rn(X, tc[t]));
       }
+      if (lane == 0)
+        xmask[p] = nzmask;
       __syncwarp();
       // rectangular part: columns k < 32p (lanes over k), rows of this panel descending
 #pragma unroll
       for (int q = 0; q < MAXQ; q++)
       {
-        if (q < p)
+        if (q < p && nzmask)
         {
           const int k = 32 * q + lane;
           if (k >= sr_start)
           {
             const double *col = v.mu + mu_panel_base(p) + (size_t)k * 32;
             double a          = bm[q];
-            for (int t = 31; t >= 0; --t)
-            {
-              const int j = 32 * p + t;
-              if (j >= sr_end || j < sr_start)
-                continue;
-              const double X = s.xs[j];
-              if (X == 0.0)
-                continue;
-              a = __dsub_rn(a, __dmul_rn(X, col[t]));
-            }
+            double cv[32];  // mu(32p + t, k), t = 0..31: 32 independent loads in flight
+#pragma unroll
+            for (int t = 0; t < 32; t++)
+              cv[t] = ((nzmask >> t) & 1u) ? col[t] : 0.0;
+#pragma unroll
+            for (int t = 31; t >= 0; --t)  // rows with X != 0 only, still in descending order
+              if ((nzmask >> t) & 1u)
+                a = __dsub_rn(a, __dmul_rn(s.xs[32 * p + t], cv[t]));
             bm[q] = a;
           }
         }
@@ -115,39 +147,83 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
     }
     __syncwarp();
     // integer row operations b_kappa += (-X_j) * 2^expo_j * b_j, fused over j (row_addmul_we, gso.cpp:236-262).
-    // Integer additions commute exactly (mod 2^64), so one pass over the columns applies all j.
-    // First convert every X_j with get_si_exp_we (lanes over j): lx -> aux[j] (bit pattern), shift -> murow[j].
-    for (int j = sr_start + lane; j < sr_end; j += 32)
+    // Integer additions commute exactly (mod 2^64), so one pass over the columns applies all j.  Only the rows with
+    // X_j != 0 are visited (typically a handful): compact them first — lx -> aux[t], shift -> murow[t], row -> xs'[t].
+    int nnz = 0;
     {
-      const double X = s.xs[j];
-      long expo      = 0, lx = 0;
-      if (X != 0.0)
-        lx = get_si_exp_we(-X, expo, v.row_expo_en ? (long)(ek - v.row_expo[j]) : 0);
-      s.aux[j]   = __longlong_as_double((long long)lx);
-      s.murow[j] = __longlong_as_double((long long)expo);
+      const int p_hi = (sr_end - 1) >> 5, p_lo = sr_start >> 5;
+      for (int p = p_hi; p >= p_lo; --p)
+      {
+        const unsigned m = xmask[p];
+        if ((m >> lane) & 1u)
+        {
+          const int j    = 32 * p + lane;
+          const int slot = nnz + (lane == 31 ? 0 : __popc(m >> (lane + 1)));  // descending j within the panel
+          const double X = s.xs[j];
+          long expo      = 0;
+          const long lx  = get_si_exp_we(-X, expo, v.row_expo_en ? (long)(ek - v.row_expo[j]) : 0);
+          s.aux[slot]    = __longlong_as_double((long long)lx);
+          s.murow[slot]  = __longlong_as_double(((long long)expo << 32) | (unsigned)j);
+        }
+        nnz += __popc(m);
+      }
     }
     __syncwarp();
+    if (nnz)
     {
+      // lane l owns columns l, l+32, ... of a group of up to 8*32 columns: 4 source rows x 8 column chunks = 32 loads in
+      // flight per round (the source rows are contiguous, every load is a 256-byte coalesced line)
       const int nc           = v.meta[M_NKC];
       unsigned long long *bk = (unsigned long long *)(v.b + (size_t)kappa * v.ldb);
-      for (int c0 = 0; c0 < nc; c0 += 32)
+      for (int cg0 = 0; cg0 < nc; cg0 += 256)
       {
-        const int c            = c0 + lane;
-        unsigned long long acc = (c < nc) ? bk[c] : 0ull;
-        for (int j = sr_end - 1; j >= sr_start; --j)
+        unsigned long long acc[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++)
         {
-          const unsigned long long lx = (unsigned long long)__double_as_longlong(s.aux[j]);
-          if (lx == 0ull)
-            continue;
-          const long long expo = __double_as_longlong(s.murow[j]);
-          if (c < nc)
-          {
-            unsigned long long t = ((const unsigned long long *)(v.b + (size_t)j * v.ldb))[c] * lx;
-            acc += (expo >= 64 ? 0ull : (t << expo));
-          }
+          const int c = cg0 + 32 * w + lane;
+          acc[w]      = (c < nc) ? bk[c] : 0ull;
         }
-        if (c < nc)
-          bk[c] = acc;
+        for (int t0 = 0; t0 < nnz; t0 += 4)
+        {
+          unsigned long long bv[4][8], lxv[4];
+          int ev[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+          {
+            const int t = t0 + u;
+            lxv[u] = 0ull, ev[u] = 0;
+            const unsigned long long *src = bk;
+            if (t < nnz)
+            {
+              lxv[u]             = (unsigned long long)__double_as_longlong(s.aux[t]);
+              const long long pk = __double_as_longlong(s.murow[t]);
+              ev[u]              = (int)(pk >> 32);
+              src = (const unsigned long long *)(v.b + (size_t)(int)(pk & 0xffffffffll) * v.ldb);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; w++)
+            {
+              const int c = cg0 + 32 * w + lane;
+              bv[u][w]    = (t < nnz && c < nc) ? src[c] : 0ull;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 8; w++)
+            {
+              const unsigned long long tt = bv[u][w] * lxv[u];
+              acc[w] += (ev[u] >= 64 ? 0ull : (tt << ev[u]));
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+        {
+          const int c = cg0 + 32 * w + lane;
+          if (c < nc)
+            bk[c] = acc[w];
+        }
       }
     }
     __syncwarp();
@@ -260,6 +336,7 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
   const int d = kappa_end - kappa_min;
   int kappa = kappa_start + 1, zeros = 0;
   st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
+  st.cyc_update = st.cyc_babai = st.cyc_lovasz = st.cyc_move = 0;
   const double swap_threshold = delta;
   // Clean prefix: rows [0, c) are (delta, eta)-LLL-reduced with a valid GSO and untouched since the call that made
   // them so.  On such rows every iteration of the reference's loop is a no-op on the state (babai finds |mu| <= eta,
@@ -289,13 +366,33 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
       return RED_GSO_FAILURE;
     }
   }
-  const long maxe = warp_max_exp_of_b(v, lane);
-  const long long max_iter =
-      (long long)((double)d - (double)(2 * d * (d + 1)) * ((double)(maxe + 3) / log(delta)));
+  // max_iter = d - 2d(d+1)((max_exp_of_b + 3)/log delta)  (lll.cpp:78-82) needs a scan of the whole basis; it is only a
+  // safety cap, so start from its smallest possible value (max_exp_of_b = 0) and pay for the exact one only if the
+  // loop ever gets that far — same termination behaviour, no d*n scan per call.
+  long long max_iter = (long long)((double)d - (double)(2 * d * (d + 1)) * (3.0 / log(delta)));
+  bool max_iter_exact = false;
   long long iter;
-  for (iter = 0; iter < max_iter && kappa < kappa_end - zeros; iter++)
+  for (iter = 0; kappa < kappa_end - zeros; iter++)
   {
-    const int bst = warp_babai<MAXQ>(v, s, kappa, kappa, sr_start, eta, lane, st.babai_iters);
+    if (iter >= max_iter)
+    {
+      if (max_iter_exact)
+        break;
+      const long maxe = warp_max_exp_of_b(v, lane);
+      max_iter        = (long long)((double)d - (double)(2 * d * (d + 1)) * ((double)(maxe + 3) / log(delta)));
+      max_iter_exact  = true;
+      if (iter >= max_iter)
+        break;
+    }
+#ifdef B200_LLL_PROFILE
+    const long long tb_ = clock64();
+    const long long cu_ = st.cyc_update;
+#endif
+    const int bst = warp_babai<MAXQ>(v, s, kappa, kappa, sr_start, eta, lane, st.babai_iters, &st.cyc_update);
+#ifdef B200_LLL_PROFILE
+    st.cyc_babai += (clock64() - tb_) - (st.cyc_update - cu_);
+    const long long tl_ = clock64();
+#endif
     if (bst != RED_SUCCESS)
     {
       st.final_kappa = kappa, st.zeros = zeros;
@@ -332,6 +429,10 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     }
     action    = __shfl_sync(FULL, action, 0);
     new_kappa = __shfl_sync(FULL, new_kappa, 0);
+#ifdef B200_LLL_PROFILE
+    st.cyc_lovasz += clock64() - tl_;
+    const long long tm_ = clock64();
+#endif
     if (action)
     {
       st.n_swaps++;
@@ -352,6 +453,9 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     __syncwarp();
     warp_set_r(v, kappa, kappa, lov[kappa], lane);
     kappa++;
+#ifdef B200_LLL_PROFILE
+    st.cyc_move += clock64() - tm_;
+#endif
   }
   st.zeros = zeros;
   if (kappa < kappa_end - zeros)

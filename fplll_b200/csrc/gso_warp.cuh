@@ -61,6 +61,8 @@ __device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
 // FP_NR<double>::rnd_we, nr_FP_d.inl:226-233 (rint = round-half-even)
 __device__ inline double rnd_we(double x, long expo_add)
 {
+  if (expo_add == 0 && fabs(x) < 4503599627370496.0)  // |x| < 2^52: both branches below reduce to rint(x)
+    return rint(x);
   if (fexponent(x) + expo_add >= 53)
     return x;
   return ldexp(rint(ldexp(x, (int)expo_add)), (int)-expo_add);

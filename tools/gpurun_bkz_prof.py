@@ -1,5 +1,7 @@
 import sys, time, numpy as np
-sys.path.insert(0, "tests")
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 import helpers as H
 import fplll_b200 as fb
 z = H.gold("r200_lll_update_gso.npz")

@@ -1,5 +1,7 @@
 import sys, time, os, subprocess, numpy as np
-sys.path.insert(0, "tests")
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 import helpers as H
 from fplll_b200 import enumeration as en
 from test_enum_oracle import gso_block
