@@ -155,7 +155,7 @@ def hh_extras(local):
         from fplll_b200.householder import MatHouseholder
         d = n = 400
         i = d - 1
-        B = 2368
+        B = 2960  # = the resident warps of hk_update_R<14> on 148 SMs (one full wave)
         rng = np.random.default_rng(7)
         b = rng.integers(-(1 << 20), 1 << 20, size=(1, d, n), dtype=np.int64)
         m = MatHouseholder(np.broadcast_to(b, (B, d, n)), 5, device=local, keep_history=False)
@@ -184,12 +184,22 @@ def bkz_extras(local):
     try:
         import fplll_b200 as fb
         g = np.load(os.path.join(ROOT, "tests", "golden", "r200_lll_update_gso.npz"))
-        b = g["b"].copy()
-        t0 = time.perf_counter()
-        st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
-                                                    max_loops=1, seed=1), devices=[local])
+        # fp64 BKZ on this basis is fragile in the reference itself: its own bkz_reduction dies with "infinite loop in
+        # babai" (RedStatus 3) for 2 of 5 RNG seeds within one tour (measured with oracle/_ref), so a
+        # failed attempt is retried with the next rerandomisation seed, every attempt is reported
+        attempts = []
+        for seed in (1, 2, 3):
+            b = g["b"].copy()
+            t0 = time.perf_counter()
+            st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default",
+                                                        flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS, max_loops=1, seed=seed),
+                                         devices=[local])
+            attempts.append({"seed": seed, "status": int(st), "wall_seconds": time.perf_counter() - t0})
+            if st == 8:
+                break
         out = {"workload": "BKZ-60, 1 tour, default strategies, dim-200 knapsack (LLL-reduced latticegen r 200 2000)",
-               "status": int(st), "wall_seconds": time.perf_counter() - t0, "sec_lll_sizered": stats["sec_lll"],
+               "attempts": attempts,
+               "status": int(st), "wall_seconds": attempts[-1]["wall_seconds"], "sec_lll_sizered": stats["sec_lll"],
                "sec_enum": stats["sec_enum"], "enum_nodes": int(stats["enum_nodes"]), "enum_calls": int(stats["enum_calls"]),
                "r00_before": stats["r00_before"], "r00_after": stats["r00_after"], "slope_after": stats["slope_after"]}
         from oracle import oracle as O
@@ -327,6 +337,28 @@ def main():
     h2d = B * N_COLS * 8
     d2h = 2 * B * D * 8 + B * 4
 
+    # N > 1: the enumeration is the part of the path that shards — every rank walks its share of the subtree roots of
+    # the same BKZ-60 block (roots r with r % world == rank), results merged with NCCL (fplll_b200/dist.py)
+    enum_dist = None
+    if dist and not a.no_extras:
+        try:
+            from fplll_b200.dist import enumerate_svp_distributed
+            z = np.load(os.path.join(ROOT, "tests", "golden", "enum_r200_b60_pruned_140.npz"))
+            enumerate_svp_distributed(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), device_index=local)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = enumerate_svp_distributed(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), device_index=local)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            n = int(res["nodes"].sum())
+            enum_dist = {"workload": "SVP enumeration of a BKZ-60 block of the dim-200 basis, subtree roots sharded over "
+                                     "%d ranks, merged with NCCL" % world, "nodes": n,
+                         "nodes_equal_reference": n == int(z["nodes"].sum()), "seconds_max_over_ranks": float(dt[0]),
+                         "nodes_per_s": n / float(dt[0])}
+        except Exception as ex:
+            enum_dist = {"error": str(ex)[:300]}
     if rank == 0:
         peak, peak_src = peaks()
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
@@ -343,6 +375,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s / a.steps * 1e3},
                 "gpu_launches": 2 * a.steps, "clocks": clocks}
+        if not a.no_extras and world > 1 and enum_dist is not None:
+            line["enum"] = enum_dist
         if not a.no_extras and world == 1:
             line["enum"] = enum_extras(local)
             line["householder"] = hh_extras(local)

@@ -232,7 +232,10 @@ __device__ inline void w_update_R_last(const HView &v, int i, double *sP, int la
   __syncwarp();
 }
 
-// update_R(i, last_j), householder.cpp:151-184
+// update_R(i, last_j), householder.cpp:151-184.  NPL = elements of a row each lane owns (n <= 32*NPL): the lane's
+// slice of V_j lives in registers, and the slice of V_{j+1} is requested BEFORE the serial summation of reflection j,
+// so the HBM latency of the next row hides behind the ordered chain of the current one.
+template <int NPL>
 __device__ inline void w_update_R(const HView &v, int i, int last_j, double *sR, double *sP, int lane)
 {
   const int n = v.n;
@@ -243,35 +246,59 @@ __device__ inline void w_update_R(const HView &v, int i, int last_j, double *sR,
       sR[k] = Rr[k];
     __syncwarp();
     double *hrow = v.keep_hist ? v.hist + (size_t)v.hslot[i] * n * n : nullptr;
+    double vk[NPL], vn[NPL];
+    if (i > 0)
+    {
+#pragma unroll
+      for (int u = 0; u < NPL; u++)
+      {
+        const int k = 32 * u + lane;  // row 0 starts at column 0
+        vk[u]       = (k < n) ? v.V[k] : 0.0;
+      }
+    }
     for (int j = 0; j < i; j++)
     {
-      const double *Vj = v.V + (size_t)j * n;
-      // products V(j,k) * R(i,k), k = j..n-1 (coalesced row sweep), then the ordered sum
-      double vk[8];
-      int cnt = 0;
-      for (int k = j + lane; k < n; k += 32, cnt++)
+      // lane's columns of reflection j: k = kb + 32u + lane, kb = j rounded down to a multiple of 32
+      const int kb = j & ~31;
+      if (j + 1 < i)
       {
-        const double x = Vj[k];
-        if (cnt < 8)
-          vk[cnt] = x;
-        sP[k] = __dmul_rn(x, sR[k]);
+        const double *Vn = v.V + (size_t)(j + 1) * n;
+        const int kbn    = (j + 1) & ~31;
+#pragma unroll
+        for (int u = 0; u < NPL; u++)
+        {
+          const int k = kbn + 32 * u + lane;
+          vn[u]       = (k >= j + 1 && k < n) ? Vn[k] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NPL; u++)
+      {
+        const int k = kb + 32 * u + lane;
+        if (k >= j && k < n)
+          sP[k] = __dmul_rn(vk[u], sR[k]);
       }
       __syncwarp();
       double f0 = chain_sum(sP, j, n, lane);
       f0        = -f0;
-      // R(i,k) += V(j,k) * f0  (element-wise, order irrelevant), then R(i,j) *= sigma[j]
-      cnt = 0;
-      for (int k = j + lane; k < n; k += 32, cnt++)
+#pragma unroll
+      for (int u = 0; u < NPL; u++)
       {
-        const double x = (cnt < 8) ? vk[cnt] : Vj[k];
-        double r       = __dadd_rn(sR[k], __dmul_rn(x, f0));
-        if (k == j)
-          r = __dmul_rn(v.sigma[j], r);
-        sR[k] = r;
-        if (hrow)
-          hrow[(size_t)j * n + k] = r;  // R_history[i][j][k] = R(i,k), k >= j
+        const int k = kb + 32 * u + lane;
+        if (k >= j && k < n)
+        {
+          double r = __dadd_rn(sR[k], __dmul_rn(vk[u], f0));
+          if (k == j)
+            r = __dmul_rn(v.sigma[j], r);
+          sR[k] = r;
+          if (hrow)
+            hrow[(size_t)j * n + k] = r;  // R_history[i][j][k] = R(i,k), k >= j
+        }
       }
       __syncwarp();
+#pragma unroll
+      for (int u = 0; u < NPL; u++)
+        vk[u] = vn[u];
     }
     for (int k = lane; k < n; k += 32)
       Rr[k] = sR[k];
@@ -392,13 +419,26 @@ __global__ void hk_refresh_R(HBatch S, int i)
   if (hsetup(S, v, sR, sP, lane))
     w_refresh_R(v, i, lane);
 }
-__global__ void hk_update_R(HBatch S, int i, int last_j)
+template <int NPL> __global__ void hk_update_R(HBatch S, int i, int last_j)
 {
   HView v;
   double *sR, *sP;
   int lane;
   if (hsetup(S, v, sR, sP, lane))
-    w_update_R(v, i, last_j, sR, sP, lane);
+    w_update_R<NPL>(v, i, last_j, sR, sP, lane);
+}
+static void launch_update_R(const HBatch &S, int grid, size_t smem, cudaStream_t st, int i, int last_j)
+{
+  // a lane's slice of a row must fit NPL registers even when the row starts in the middle of a 32-column group
+  const int need = (S.n + 31) / 32 + 1;
+  if (need <= 4)
+    hk_update_R<4><<<grid, HW * 32, smem, st>>>(S, i, last_j);
+  else if (need <= 8)
+    hk_update_R<8><<<grid, HW * 32, smem, st>>>(S, i, last_j);
+  else if (need <= 14)
+    hk_update_R<14><<<grid, HW * 32, smem, st>>>(S, i, last_j);
+  else
+    hk_update_R<32><<<grid, HW * 32, smem, st>>>(S, i, last_j);
 }
 __global__ void hk_update_R_last(HBatch S, int i)
 {
@@ -555,7 +595,8 @@ int b200hh_create(b200hh_t **out, int batch, int d, int n, int flags, int device
   CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->smem = (size_t)HW * 2 * ((n + 1) & ~1) * sizeof(double);
   const void *fns[] = {(const void *)hk_init,        (const void *)hk_refresh_R_bf, (const void *)hk_refresh_R,
-                       (const void *)hk_update_R,    (const void *)hk_update_R_last, (const void *)hk_size_reduce,
+                       (const void *)hk_update_R<4>, (const void *)hk_update_R<8>, (const void *)hk_update_R<14>,
+                       (const void *)hk_update_R<32>, (const void *)hk_update_R_last, (const void *)hk_size_reduce,
                        (const void *)hk_swap,        (const void *)hk_recover_R};
   for (const void *f : fns)
     CKH(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -634,7 +675,7 @@ int b200hh_refresh_R(b200hh_t *h, int i)
 }
 int b200hh_update_R(b200hh_t *h, int i, int last_j)
 {
-  HH_CALL(i >= 0 && i < h->S.d, (hk_update_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i, last_j)))
+  HH_CALL(i >= 0 && i < h->S.d && h->S.n <= 32 * 31, launch_update_R(h->S, hgrid(h), h->smem, h->stream, i, last_j))
 }
 int b200hh_update_R_last(b200hh_t *h, int i)
 {
@@ -723,7 +764,7 @@ int b200hh_time_update_R(b200hh_t *h, int i, int reps, float *ms_update_mean)
   {
     hk_refresh_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i);
     CKH(cudaEventRecord(ev[2 * r], h->stream));
-    hk_update_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i, 0);
+    launch_update_R(h->S, hgrid(h), h->smem, h->stream, i, 0);
     CKH(cudaEventRecord(ev[2 * r + 1], h->stream));
   }
   CKH(cudaStreamSynchronize(h->stream));

@@ -626,6 +626,12 @@ int main(int argc, char **argv)
       red.hlll();
       printf("hlll_long status=%d sec=%.6f\n", red.get_status(), now() - t0);
     }
+    else if (c == "seed")
+    {
+      unsigned long sd;
+      is >> sd;
+      RandGen::init_with_seed(sd);
+    }
     else if (c == "time_update_row")
     {
       int i, reps, inv;
