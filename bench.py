@@ -174,7 +174,7 @@ def hh_extras(local):
     return out
 
 
-def bkz_extras(local):
+def bkz_extras(local, devices=None, with_ref=True):
     """The BKZ half of the BASELINE metric: wall-seconds of ONE tour of BKZ-60 (strategies/default.json table, fp64,
     BKZ_NO_LLL | BKZ_MAX_LOOPS=1) on the wrapper-LLL-reduced latticegen r 200 2000 basis (tests/golden), device GSO/LLL +
     device enumeration, next to the reference's bkz_reduction on the same input on the host (1 thread = the CLI default,
@@ -193,17 +193,17 @@ def bkz_extras(local):
             t0 = time.perf_counter()
             st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default",
                                                         flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS, max_loops=1, seed=seed),
-                                         devices=[local])
+                                         devices=devices or [local])
             attempts.append({"seed": seed, "status": int(st), "wall_seconds": time.perf_counter() - t0})
             if st == 8:
                 break
         out = {"workload": "BKZ-60, 1 tour, default strategies, dim-200 knapsack (LLL-reduced latticegen r 200 2000)",
-               "attempts": attempts,
+               "devices": len(devices or [local]), "attempts": attempts,
                "status": int(st), "wall_seconds": attempts[-1]["wall_seconds"], "sec_lll_sizered": stats["sec_lll"],
                "sec_enum": stats["sec_enum"], "enum_nodes": int(stats["enum_nodes"]), "enum_calls": int(stats["enum_calls"]),
                "r00_before": stats["r00_before"], "r00_after": stats["r00_after"], "slope_after": stats["slope_after"]}
         from oracle import oracle as O
-        if O.have_ref():
+        if with_ref and O.have_ref():
             tmp = tempfile.mkdtemp(prefix="bench_bkz_")
             mat = os.path.join(tmp, "b.txt")
             O.write_matrix(mat, g["b"])
@@ -377,6 +377,10 @@ def main():
                 "gpu_launches": 2 * a.steps, "clocks": clocks}
         if not a.no_extras and world > 1 and enum_dist is not None:
             line["enum"] = enum_dist
+            if not a.no_bkz:
+                # BKZ-60 wall-seconds at N GPUs: one driver (rank 0), GSO/LLL on its GPU, every enumeration's subtree
+                # roots dealt over all N devices of the box (include/b200bkz.h: devices[])
+                line["bkz60"] = bkz_extras(local, devices=list(range(world)), with_ref=False)
         if not a.no_extras and world == 1:
             line["enum"] = enum_extras(local)
             line["householder"] = hh_extras(local)

@@ -46,9 +46,11 @@ thread_local std::string g_err;
 
 constexpr int SOL_CAP    = 4096;
 constexpr int THREADS    = 128;
+constexpr int THREADS_XS = 512;      // upper bound of the CTA size of the x-in-shared-memory variant (one CTA per SM)
 constexpr int MIN_ROOTS  = 256;      // host breadth phase: grow T until at least this many roots (the device multiplies
                                     // them by work splitting, a round costs one grid barrier) ...
 constexpr int MAX_ROOTS  = 1 << 18;  // ... but never beyond this
+constexpr int SMEM_XS_MAX = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 constexpr unsigned TASK_CAP = 1u << 21;  // device task queue capacity (tasks of all rounds)
 
 struct SolRec
@@ -75,6 +77,7 @@ struct EnumArgs
   int *txq[2];                 // [TASK_CAP * dstride] coefficients by absolute level (entries > lvl are meaningful)
   unsigned n_first;            // number of tasks of round 0 (the host's subtree roots, in half 0)
   unsigned *ctr;               // device counters: [0] ticket, [1] append position, [2] tasks of the current round
+  unsigned yield_nodes;          // a walker re-checks the split / yield conditions every this many nodes
   unsigned budget0, budget_mul;  // nodes a walker may visit before it must split: budget0 * mul^round (capped)
   unsigned long long *A_bits;  // [0] radius (bit pattern of a positive double), [1] best-so-far in fixed-radius mode
   unsigned long long *nodes;   // [d]
@@ -99,16 +102,27 @@ __device__ inline double next_sibling(double x, double c, double pdk)
 // Persistent cooperative kernel: ALL rounds of one enumeration run inside one launch, separated by grid-wide barriers
 // (a round = every walker works off the current half of the task queue, walkers that split or yield append to the other
 // half).  One launch per Enumeration::enumerate call instead of one launch + host synchronisation per round.
-template <int ML>
-__global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
+//
+// XS = true (dim <= 64, every BKZ block size in use): the coefficient vectors x[] of all walkers of the CTA live in
+// SHARED memory ([level][thread], conflict-free) — the centre chain reads x[j] d-k times per node, and with x[] in
+// thread-local memory that traffic (L1 misses for 3/4 of it, ~1.6 KB of L2 reads per node) was what bounded the first
+// version (profiles/r1_enum_ncu.txt).  One CTA per SM then shares a single copy of mu^T.
+// Both variants also keep pre[k] = the part of level k's centre chain that only involves the task's FIXED coefficients
+// (j > top0): it is computed the first time the walker reaches level k inside a task and is the exact prefix of the
+// reference's descending chain, so the remaining chain is top0-k long instead of d-1-k.
+template <int ML, bool XS>
+__global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
 {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sm[];
-  const int d = a.d;
-  double *s_mut = sm, *s_r = sm + (size_t)d * d, *s_p = s_r + d;
+  const int d  = a.d;
+  const int ds = XS ? (d | 1) : d;  // odd row stride: walkers on different levels read different rows of mu^T
+  double *s_mut = sm, *s_r = sm + (size_t)d * ds, *s_p = s_r + d;
+  double *s_x = s_p + d + threadIdx.x;  // XS: x[j] of this thread at s_x[j * blockDim.x]
+  const int xstr = blockDim.x;
   for (int t = threadIdx.x; t < d * d; t += blockDim.x)
-    s_mut[t] = a.mut[t];
+    s_mut[(t / d) * ds + (t % d)] = a.mut[t];
   for (int t = threadIdx.x; t < d; t += blockDim.x)
   {
     s_r[t] = a.rdiag[t];
@@ -116,8 +130,16 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
   }
   __syncthreads();
 
-  double x[ML], cen[ML], pd[ML];
+  double xl[XS ? 1 : ML], cen[ML], pd[ML], pre[ML];
   unsigned cnt[ML];
+  auto getx = [&](int j) -> double { return XS ? s_x[(size_t)j * xstr] : xl[XS ? 0 : j]; };
+  auto setx = [&](int j, double val) {
+    if (XS)
+      s_x[(size_t)j * xstr] = val;
+    else
+      xl[XS ? 0 : j] = val;
+  };
+  int top0 = 0, pvalid = 0;
 #pragma unroll 1
   for (int k = 0; k < d; k++)
     cnt[k] = 0;
@@ -133,14 +155,20 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
   TaskHdr *hdr_out      = a.hdrq[(rno + 1) & 1];
   int *tx_out           = a.txq[(rno + 1) & 1];
   unsigned *ticket = a.ctr, *tail = a.ctr + 1;
+  const unsigned total_warps  = gridDim.x * (blockDim.x >> 5);
+  const unsigned lanes_allowed = min(32u, max(1u, (end + total_warps - 1) / total_warps));
   int k        = -2;  // -2: idle (needs a task)
   int top      = 0;   // highest level this walker still owns
   unsigned n   = 0;   // nodes since the last split
-  unsigned next_check = 64;
+  unsigned next_check = a.yield_nodes;
   for (;;)
   {
     if (k == -2)
     {
+      // a round with fewer tasks than lanes is spread over WARPS first: 32 walkers of one warp sit on different
+      // levels and serialise each other (SIMT divergence), a lone walker in a warp runs at full single-thread speed
+      if ((threadIdx.x & 31u) >= lanes_allowed)
+        break;
       const unsigned t = atomicAdd(ticket, 1u);
       if (t >= end)
         break;
@@ -148,6 +176,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
       const int4 *tx4 = (const int4 *)(tx_in + (size_t)t * a.dstride);
       A               = __longlong_as_double(*(volatile unsigned long long *)a.A_bits);
       top = k = h.lvl;
+      top0 = pvalid = k;
       // prefix x[lvl+1 .. d-1]: 128-bit loads, 4 in flight (a walker that starts a task stalls its whole warp, so
       // this must cost one memory latency, not d of them)
 #pragma unroll 4
@@ -156,23 +185,24 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
         const int4 q = tx4[j4];
         const int j  = 4 * j4;
         if (j > k && j < d)
-          x[j] = (double)q.x;
+          setx(j, (double)q.x);
         if (j + 1 > k && j + 1 < d)
-          x[j + 1] = (double)q.y;
+          setx(j + 1, (double)q.y);
         if (j + 2 > k && j + 2 < d)
-          x[j + 2] = (double)q.z;
+          setx(j + 2, (double)q.z);
         if (j + 3 > k && j + 3 < d)
-          x[j + 3] = (double)q.w;
+          setx(j + 3, (double)q.w);
       }
       pd[k]  = h.pd;
       cen[k] = h.cen;
-      x[k]   = h.xs;
+      setx(k, h.xs);
       n      = 0;
-      next_check = 64;
+      next_check = a.yield_nodes;
     }
 
     // ---- one step of enumerate_loop (enumerate_base.cpp:193-254) ----
-    const double alphak  = __dsub_rn(x[k], cen[k]);
+    const double xk      = getx(k);
+    const double alphak  = __dsub_rn(xk, cen[k]);
     const double newdist = __dadd_rn(pd[k], __dmul_rn(__dmul_rn(alphak, alphak), s_r[k]));
     bool up              = true;
     if (newdist <= __dmul_rn(s_p[k], A))
@@ -195,7 +225,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
               s->dist   = newdist;
 #pragma unroll 1
               for (int j = 0; j < d; j++)
-                s->x[j] = (int)x[j];
+                s->x[j] = (int)getx(j);
             }
           }
           if (!a.fixed_radius)
@@ -207,14 +237,26 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
       {
         --k;
         // centre: the reference's chain ((0 - x[d-1] mu) - x[d-2] mu) - ... - x[k+1] mu, descending j
-        double nc = 0.0;
-        const double *mrow = s_mut + (size_t)k * d;
+        double nc;
+        const double *mrow = s_mut + (size_t)k * ds;
+        if (k < pvalid)
+        {
+          // first visit of level k inside this task (k == pvalid - 1): the fixed part of the chain, j = d-1 .. top0+1
+          nc = 0.0;
 #pragma unroll 4
-        for (int j = d - 1; j > k; --j)
-          nc = __dsub_rn(nc, __dmul_rn(x[j], mrow[j]));
+          for (int j = d - 1; j > top0; --j)
+            nc = __dsub_rn(nc, __dmul_rn(getx(j), mrow[j]));
+          pre[k] = nc;
+          pvalid = k;
+        }
+        else
+          nc = pre[k];
+#pragma unroll 4
+        for (int j = top0; j > k; --j)
+          nc = __dsub_rn(nc, __dmul_rn(getx(j), mrow[j]));
         cen[k] = nc;
         pd[k]  = newdist;
-        x[k]   = round(nc);
+        setx(k, round(nc));
         up     = false;
       }
     }
@@ -224,7 +266,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
       if (k > top)
         k = -2;  // everything this walker owned is done
       else
-        x[k] = next_sibling(x[k], cen[k], pd[k]);
+        setx(k, next_sibling(getx(k), cen[k], pd[k]));
     }
     else if (n >= next_check)
     {
@@ -235,7 +277,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
       //    ancestor's remaining siblings plus its current position become tasks of the next round — so the tail of
       //    a round is bounded by ~64 nodes instead of by the largest subtree.
       const bool dry = (*(volatile unsigned *)ticket >= end);
-      next_check     = n + 64;
+      next_check     = n + a.yield_nodes;
       if (dry || n >= budget)
       {
         int jj = top, given = 0;
@@ -244,7 +286,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
         {
           // siblings come in order of increasing distance from the centre: if the next one is already outside the
           // bound there is nothing left at this level
-          const double nx = next_sibling(x[jj], cen[jj], pd[jj]);
+          const double nx = next_sibling(getx(jj), cen[jj], pd[jj]);
           const double al = __dsub_rn(nx, cen[jj]);
           const double nd = __dadd_rn(pd[jj], __dmul_rn(__dmul_rn(al, al), s_r[jj]));
           if (!(nd <= __dmul_rn(s_p[jj], A)))
@@ -261,7 +303,7 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
           int *tx       = tx_out + (size_t)slot * a.dstride;
 #pragma unroll 4
           for (int j = jj + 1; j < d; j++)
-            tx[j] = (int)x[j];
+            tx[j] = (int)getx(j);
           given++;
         }
         top = jj;  // levels above jj are donated or exhausted; the walker keeps the siblings of levels <= jj
@@ -271,17 +313,17 @@ __global__ void __launch_bounds__(THREADS) k_enum(EnumArgs a)
           if (slot < TASK_CAP)
           {
             TaskHdr h;
-            h.pd = pd[k], h.cen = cen[k], h.xs = x[k], h.lvl = k, h.pad = 0;
+            h.pd = pd[k], h.cen = cen[k], h.xs = getx(k), h.lvl = k, h.pad = 0;
             hdr_out[slot] = h;
             int *tx       = tx_out + (size_t)slot * a.dstride;
 #pragma unroll 4
             for (int j = k + 1; j < d; j++)
-              tx[j] = (int)x[j];
+              tx[j] = (int)getx(j);
             k = -2;  // yielded: this walker is idle (and the round is dry, so it will leave the loop)
           }
         }
         n          = 0;
-        next_check = 64;
+        next_check = a.yield_nodes;
       }
     }
     if (((++steps) & 63) == 0 && !a.fixed_radius)
@@ -426,8 +468,9 @@ int get_ctx(int device, DevCtx **out)
   CKE(cudaMallocHost(&c.h_sols, SOL_CAP * sizeof(SolRec)));
   CKE(cudaMallocHost(&c.h_words, 8 * sizeof(unsigned long long)));
   CKE(cudaMallocHost(&c.h_nodes, B200ENUM_MAX_DIM * sizeof(unsigned long long)));
-  CKE(cudaFuncSetAttribute((const void *)k_enum<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  CKE(cudaFuncSetAttribute((const void *)k_enum<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CKE(cudaFuncSetAttribute((const void *)k_enum<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CKE(cudaFuncSetAttribute((const void *)k_enum<160, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CKE(cudaFuncSetAttribute((const void *)k_enum<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_XS_MAX));
   g_ctx.push_back(c);
   *out = &g_ctx.back();
   return 0;
@@ -592,8 +635,22 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
   // grid barrier.
   static const unsigned budget0 = getenv("B200_ENUM_BUDGET0") ? atoi(getenv("B200_ENUM_BUDGET0")) : 64;
   static const unsigned budget_mul = getenv("B200_ENUM_BUDGET_MUL") ? atoi(getenv("B200_ENUM_BUDGET_MUL")) : 4;
+  static const unsigned yield_nodes = getenv("B200_ENUM_YIELD") ? atoi(getenv("B200_ENUM_YIELD")) : 64;
   static const int bpsm = getenv("B200_ENUM_BLOCKS_PER_SM") ? atoi(getenv("B200_ENUM_BLOCKS_PER_SM")) : 4;
-  const size_t smem = cfg_n * sizeof(double);
+  static const int use_xs = getenv("B200_ENUM_XS") ? atoi(getenv("B200_ENUM_XS")) : 1;
+  static const int xs_threads_cap = getenv("B200_ENUM_XS_THREADS") ? atoi(getenv("B200_ENUM_XS_THREADS")) : 320;
+  const bool xs = use_xs && d <= 64;
+  // x-in-shared variant: one CTA per SM, as many walkers as fit next to mu^T (odd row stride) + rdiag + pruning
+  const size_t cfg_smem = xs ? ((size_t)d * (d | 1) + 2 * d) * sizeof(double) : cfg_n * sizeof(double);
+  int threads = THREADS;
+  if (xs)
+  {
+    threads = (int)((SMEM_XS_MAX - cfg_smem) / ((size_t)d * sizeof(double)));
+    threads = std::min(std::min(threads, xs_threads_cap), THREADS_XS) & ~31;
+    if (threads < 32)
+      threads = 32;
+  }
+  const size_t smem = cfg_smem + (xs ? (size_t)threads * d * sizeof(double) : 0);
   for (int q = 0; q < ndev; q++)
   {
     if (tail[q] == 0)
@@ -606,20 +663,21 @@ int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag
     a.txq[0] = c->d_tx, a.txq[1] = c->d_tx + (size_t)TASK_CAP * dstride;
     a.n_first = tail[q];
     a.ctr = (unsigned *)(c->d_words + 4), a.sol_count = (unsigned *)(c->d_words + 3) + 1;
-    a.budget0 = budget0, a.budget_mul = budget_mul;
+    a.budget0 = budget0, a.budget_mul = budget_mul, a.yield_nodes = yield_nodes;
     a.A_bits = c->d_words, a.leaves = c->d_words + 2, a.nodes = c->d_nodes, a.sols = c->d_sols;
     a.fixed_radius = fixed ? 1 : 0;
     int occ = 0;
-    const void *fn = d <= 64 ? (const void *)k_enum<64> : (const void *)k_enum<160>;
-    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, THREADS, smem));
+    const void *fn = xs ? (const void *)k_enum<64, true>
+                        : (d <= 64 ? (const void *)k_enum<64, false> : (const void *)k_enum<160, false>);
+    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
     if (occ < 1)
     {
       g_err = "b200enum_run: kernel does not fit on an SM";
       return B200ENUM_ECUDA;
     }
-    const int blocks = c->sms * std::min(occ, bpsm);  // every CTA must be resident (grid-wide barrier)
+    const int blocks = c->sms * (xs ? 1 : std::min(occ, bpsm));  // every CTA must be resident (grid-wide barrier)
     void *params[]   = {(void *)&a};
-    CKE(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(THREADS), params, smem, c->stream));
+    CKE(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), params, smem, c->stream));
   }
   int rounds = 0;
   std::vector<uint64_t> tot(d, 0);

@@ -460,13 +460,8 @@ __global__ void hk_size_reduce(HBatch S, int k, int e, int st, int *reduced)
     reduced[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = r ? 1 : 0;
 }
 // swap(i, j), householder.cpp:372-398
-__global__ void hk_swap(HBatch S, int i, int j)
+__device__ inline void w_swap(const HView &v, int i, int j, int lane)
 {
-  HView v;
-  double *sR, *sP;
-  int lane;
-  if (!hsetup(S, v, sR, sP, lane))
-    return;
   if (lane == 0 && i < v.meta[HM_NKR])
     v.meta[HM_NKR] = i;  // invalidate_row(i)
   for (int c = lane; c < v.n; c += 32)
@@ -496,15 +491,19 @@ __global__ void hk_swap(HBatch S, int i, int j)
     long le = v.ensb[i];
     v.ensb[i] = v.ensb[j], v.ensb[j] = le;
   }
+  __syncwarp();
 }
-// recover_R(i), householder.h:597-608
-__global__ void hk_recover_R(HBatch S, int i)
+__global__ void hk_swap(HBatch S, int i, int j)
 {
   HView v;
   double *sR, *sP;
   int lane;
-  if (!hsetup(S, v, sR, sP, lane))
-    return;
+  if (hsetup(S, v, sR, sP, lane))
+    w_swap(v, i, j, lane);
+}
+// recover_R(i), householder.h:597-608
+__device__ inline void w_recover_R(const HView &v, int i, int lane)
+{
   const int n = v.n;
   const double *hrow = v.hist + (size_t)v.hslot[i] * n * n;
   double *Rr = v.R + (size_t)i * n;
@@ -512,6 +511,202 @@ __global__ void hk_recover_R(HBatch S, int i)
     Rr[k] = (k < i - 1) ? hrow[(size_t)k * n + k] : hrow[(size_t)(i - 1) * n + k];
   if (lane == 0)
     v.meta[HM_UPDATED] = 1;
+  __syncwarp();
+}
+__global__ void hk_recover_R(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane))
+    w_recover_R(v, i, lane);
+}
+
+// ---- HLLLReduction::hlll(), hlll.cpp:25-171, whole loop on the device: one warp per lattice -------------------------
+struct HlllArgs
+{
+  double delta, theta;
+  double *dR, *eR, *prevR;  // B x d each
+  int *prevE;               // B x d
+  int *status;              // B
+  unsigned long long *iters;  // B (loop iterations, diagnostics)
+  unsigned long long max_iter;
+};
+
+// size_reduction(kappa, kappa, 0), hlll.cpp:262-354 (default branch: approx = 0.1)
+template <int NPL> __device__ inline void w_hlll_size_reduction(const HView &v, int kappa, double *sR, double *sP, int lane)
+{
+  bool prev_not_stop = true;
+  w_update_R<NPL>(v, kappa, 0, sR, sP, lane);
+  __syncwarp();
+  if (lane == 0)
+    v.meta[HM_UPDATED] = 0;  // set_updated_R_false(), hlll.cpp:322
+  __syncwarp();
+  for (;;)
+  {
+    if (!w_size_reduce(v, kappa, kappa, 0, lane))
+      return;
+    const double t    = v.nsb[kappa];
+    const long expo0  = v.ensb[kappa];
+    __syncwarp();
+    w_refresh_R_bf(v, kappa, sP, lane);
+    const double f1   = v.nsb[kappa];
+    const long expo1  = v.ensb[kappa];
+    double f0         = __dmul_rn(0.1, t);
+    f0                = ldexp(f0, (int)(expo0 - expo1));
+    const bool not_stop = (f1 <= f0);
+    w_update_R<NPL>(v, kappa, 0, sR, sP, lane);
+    if (prev_not_stop || not_stop)
+      prev_not_stop = not_stop;
+    else
+      return;
+  }
+}
+
+template <int NPL> __device__ inline int w_hlll(const HView &v, const HlllArgs &A, int l, double *sR, double *sP, int lane)
+{
+  const int d = v.d, n = v.n;
+  double *dR = A.dR + (size_t)l * d, *eR = A.eR + (size_t)l * d, *pR = A.prevR + (size_t)l * d;
+  int *pE = A.prevE + (size_t)l * d;
+  // compute_dR / compute_eR, hlll.h:147-159 (eR is delta * R(k,k) in the reference, and here)
+  auto compute_dR_eR = [&](int k) {
+    const double rkk = v.R[(size_t)k * n + k];
+    if (lane == 0)
+    {
+      dR[k] = __dmul_rn(A.delta, __dmul_rn(rkk, rkk));
+      eR[k] = __dmul_rn(A.delta, rkk);
+    }
+    __syncwarp();
+  };
+  w_refresh_R_bf(v, 0, sP, lane);
+  w_update_R_last(v, 0, sP, lane);
+  compute_dR_eR(0);
+  if (d < 2)
+    return 0;
+  int k = 1, k_max = 1, prev_k = -1;
+  w_refresh_R_bf(v, 1, sP, lane);
+  unsigned long long it = 0;
+  int status = -1;
+  for (;;)
+  {
+    if (++it > A.max_iter)
+    {
+      status = 9;  // RED_HLLL_FAILURE: iteration guard (the reference has none; protects the device from a livelock)
+      break;
+    }
+    w_hlll_size_reduction<NPL>(v, k, sR, sP, lane);
+    // verify_size_reduction(k), hlll.cpp:373-478 (default branch)
+    const double *Rk = v.R + (size_t)k * n;
+    {
+      for (int c = k + lane; c < n; c += 32)
+        sP[c] = __dmul_rn(Rk[c], Rk[c]);
+      __syncwarp();
+      double f1 = (n > k) ? sqrt(chain_sum(sP, k, n, lane)) : 0.0;  // norm_R_row(k, k, n), householder.h:572-588
+      f1        = __dmul_rn(f1, A.theta);
+      const int expo0 = v.row_expo[k];
+      bool bad = false;
+      for (int i = lane; i < k; i += 32)
+      {
+        const double f0 = fabs(Rk[i]);
+        const double f2 = __dadd_rn(f1, ldexp(eR[i], v.row_expo[i] - expo0));
+        bad |= (f0 > f2);
+      }
+      __syncwarp();
+      if (__any_sync(FULLM, bad))
+      {
+        status = 11;  // RED_HLLL_SR_FAILURE
+        break;
+      }
+    }
+    // lovasz_test(k), hlll.cpp:173-236
+    bool lov;
+    {
+      double f1 = 0.0;
+      if (k - 1 > 0)
+      {
+        for (int c = lane; c < k - 1; c += 32)
+          sP[c] = __dmul_rn(Rk[c], Rk[c]);
+        __syncwarp();
+        f1 = chain_sum(sP, 0, k - 1, lane);  // norm_square_R_row(k, 0, k-1), householder.h:554-568
+      }
+      f1 = __dsub_rn(v.nsb[k], f1);
+      const long expo1 = v.row_expo_en ? 2L * v.row_expo[k] : 0L;
+      f1  = ldexp(f1, (int)(expo1 - 2L * v.row_expo[k - 1]));
+      lov = (dR[k - 1] <= f1);
+      __syncwarp();
+    }
+    if (lov)
+    {
+      w_update_R_last(v, k, sP, lane);
+      compute_dR_eR(k);
+      const double rkk = Rk[k];
+      const int ek     = v.row_expo[k];
+      if (prev_k == k + 1)
+      {
+        const double f1 = ldexp(pR[k], pE[k] - ek);
+        if (rkk > f1)
+        {
+          status = 10;  // RED_HLLL_NORM_FAILURE
+          break;
+        }
+      }
+      prev_k = k;
+      __syncwarp();
+      if (lane == 0)
+        pR[k] = rkk, pE[k] = ek;
+      __syncwarp();
+      k++;
+      if (k < d)
+      {
+        if (k > k_max)
+        {
+          k_max = k;
+          w_refresh_R_bf(v, k, sP, lane);
+        }
+        else
+          w_refresh_R(v, k, lane);
+      }
+      else
+      {
+        status = 0;
+        break;
+      }
+    }
+    else
+    {
+      w_swap(v, k - 1, k, lane);
+      prev_k = k;
+      if (k - 1 == 0)
+      {
+        w_refresh_R(v, 0, lane);
+        w_update_R_last(v, 0, sP, lane);
+        compute_dR_eR(0);
+        w_refresh_R(v, 1, lane);
+        k = 1;
+      }
+      else
+      {
+        k--;
+        w_recover_R(v, k, lane);
+      }
+    }
+  }
+  if (lane == 0)
+    A.iters[l] = it;
+  return status;
+}
+
+template <int NPL> __global__ void hk_hlll(HBatch S, HlllArgs A)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (!hsetup(S, v, sR, sP, lane))
+    return;
+  const int l  = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int st = w_hlll<NPL>(v, A, l, sR, sP, lane);
+  if (lane == 0)
+    A.status[l] = st;
 }
 __global__ void hk_set_updated(HBatch S, int val)
 {
@@ -529,6 +724,9 @@ struct b200hh
   cudaStream_t stream;
   size_t smem;
   int *d_red;
+  double *d_hlll = nullptr;  // dR, eR, prevR: 3 x B x d
+  int *d_hlll_i = nullptr;   // prevE: B x d, status: B
+  unsigned long long *d_hlll_it = nullptr;
   std::vector<void *> allocs;
 };
 
@@ -597,7 +795,8 @@ int b200hh_create(b200hh_t **out, int batch, int d, int n, int flags, int device
   const void *fns[] = {(const void *)hk_init,        (const void *)hk_refresh_R_bf, (const void *)hk_refresh_R,
                        (const void *)hk_update_R<4>, (const void *)hk_update_R<8>, (const void *)hk_update_R<14>,
                        (const void *)hk_update_R<32>, (const void *)hk_update_R_last, (const void *)hk_size_reduce,
-                       (const void *)hk_swap,        (const void *)hk_recover_R};
+                       (const void *)hk_swap,        (const void *)hk_recover_R,   (const void *)hk_hlll<4>,
+                       (const void *)hk_hlll<8>,     (const void *)hk_hlll<14>,     (const void *)hk_hlll<32>};
   for (const void *f : fns)
     CKH(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CKH(cudaMemsetAsync(S.b, 0, (size_t)batch * d * S.ldb * 8, h->stream));
@@ -778,6 +977,54 @@ int b200hh_time_update_R(b200hh_t *h, int i, int reps, float *ms_update_mean)
   for (auto &e : ev)
     cudaEventDestroy(e);
   *ms_update_mean = (float)(tot / reps);
+  CKH(cudaGetLastError());
+  return 0;
+}
+
+int b200hh_hlll(b200hh_t *h, double delta, double eta, double theta, double c, int *status, uint64_t *iterations)
+{
+  (void)eta;  // hlll.h:155-159: eR is formed with delta in the reference; eta is not read on this code path
+  (void)c;    // sr = 2^(-c d) is read only under HOUSEHOLDER_USE_SIZE_REDUCTION_TEST (hlll.cpp:296-312)
+  if (!h || !status)
+    return B200HH_EINVAL;
+  if (!h->S.keep_hist)
+  {
+    g_err = "b200hh_hlll: the handle was created without keep_history (recover_R needs R_history)";
+    return B200HH_EINVAL;
+  }
+  CKH(cudaSetDevice(h->device));
+  const HBatch &S = h->S;
+  const size_t bd = (size_t)S.B * S.d;
+  if (!h->d_hlll)
+  {
+    int rc = hh_alloc(h, &h->d_hlll, 3 * bd);
+    rc |= hh_alloc(h, &h->d_hlll_i, bd + S.B);
+    rc |= hh_alloc(h, &h->d_hlll_it, (size_t)S.B);
+    if (rc)
+      return B200HH_ENOMEM;
+  }
+  CKH(cudaMemsetAsync(h->d_hlll, 0, 3 * bd * 8, h->stream));
+  CKH(cudaMemsetAsync(h->d_hlll_i, 0, (bd + S.B) * 4, h->stream));
+  CKH(cudaMemsetAsync(h->d_hlll_it, 0, (size_t)S.B * 8, h->stream));
+  hk_init<<<hgrid(h), HW * 32, h->smem, h->stream>>>(S);  // a fresh MatHouseholder over the current b
+  HlllArgs A;
+  A.delta = delta, A.theta = theta;
+  A.dR = h->d_hlll, A.eR = h->d_hlll + bd, A.prevR = h->d_hlll + 2 * bd;
+  A.prevE = h->d_hlll_i, A.status = h->d_hlll_i + bd, A.iters = h->d_hlll_it;
+  A.max_iter = 1000000ull + 64ull * S.d * S.d;
+  const int need = (S.n + 31) / 32 + 1;
+  if (need <= 4)
+    hk_hlll<4><<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, A);
+  else if (need <= 8)
+    hk_hlll<8><<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, A);
+  else if (need <= 14)
+    hk_hlll<14><<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, A);
+  else
+    hk_hlll<32><<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, A);
+  CKH(cudaMemcpyAsync(status, A.status, (size_t)S.B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (iterations)
+    CKH(cudaMemcpyAsync(iterations, A.iters, (size_t)S.B * 8, cudaMemcpyDeviceToHost, h->stream));
+  CKH(cudaStreamSynchronize(h->stream));
   CKH(cudaGetLastError());
   return 0;
 }

@@ -30,6 +30,7 @@ def _lib():
         L.b200hh_get_state.argtypes = [vp] + [_P(C.c_double)] * 5 + [_P(C.c_int64)] * 2 + [_P(C.c_int)]
         L.b200hh_time_update_R.argtypes = [vp, i, i, _P(C.c_float)]
         L.b200hh_sync.argtypes = [vp]
+        L.b200hh_hlll.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, _P(C.c_int), _P(C.c_uint64)]
         _done = True
     return L
 
@@ -99,7 +100,39 @@ class MatHouseholder:
         return dict(R=R, V=V, bf=bf, sigma=sg, norm_square_b=nsb, row_expo=re, expo_norm_square_b=en, b=b,
                     n_known_rows=meta[:, 0].copy(), n_known_cols=meta[:, 1].copy(), updated_R=meta[:, 2].copy())
 
+    def hlll(self, delta=0.99, eta=0.51, theta=0.001, c=0.1):
+        """HLLLReduction(m, delta, eta, theta, c, flags).hlll() (hlll.cpp:25-171), whole loop on the device.
+        Returns (status per lattice, main-loop iterations per lattice)."""
+        st = np.zeros(self.batch, np.int32)
+        it = np.zeros(self.batch, np.uint64)
+        _ck(_lib().b200hh_hlll(self._h, delta, eta, theta, c, st.ctypes.data_as(_P(C.c_int)),
+                               it.ctypes.data_as(_P(C.c_uint64))), "hlll")
+        return st, it
+
+    def get_basis(self):
+        b = np.empty((self.batch, self.d, self.n), np.int64)
+        _ck(_lib().b200hh_get_basis(self._h, b.ctypes.data_as(_P(C.c_int64))), "get_basis")
+        return b
+
     def time_update_R(self, i, reps):
         ms = C.c_float()
         _ck(_lib().b200hh_time_update_R(self._h, i, reps, C.byref(ms)), "time_update_R")
         return ms.value
+
+
+RED_HLLL_FAILURE, RED_HLLL_NORM_FAILURE, RED_HLLL_SR_FAILURE = 9, 10, 11  # defs.h:164-166
+
+
+def hlll_reduction(b, delta=0.99, eta=0.51, theta=0.001, c=0.1, device=0):
+    """hlll_reduction(ZZ_mat<long>& b, delta, eta, theta, c, HM_FAST, FT_DOUBLE) — fplll/wrapper.cpp:789-806 with
+    defaults LLL_DEF_DELTA / LLL_DEF_ETA / HLLL_DEF_THETA / HLLL_DEF_C (defs.h:143-151).  b: (d, n) or (batch, d, n)
+    int64.  Returns (reduced basis, status) — per lattice for a batch; the input array is not modified."""
+    a = np.ascontiguousarray(b, dtype=np.int64)
+    single = a.ndim == 2
+    m = MatHouseholder(a, HOUSEHOLDER_ROW_EXPO | HOUSEHOLDER_OP_FORCE_LONG, device=device, keep_history=True)
+    try:
+        st, _ = m.hlll(delta, eta, theta, c)
+        out = m.get_basis()
+    finally:
+        m.close()
+    return (out[0], int(st[0])) if single else (out, st)

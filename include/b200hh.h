@@ -60,6 +60,16 @@ int b200hh_get_state(b200hh_t *h, double *R, double *V, double *bf, double *sigm
 /* bench helper: `reps` launches of { refresh_R(i); update_R(i, 0) } timed with CUDA events on the handle's stream;
  * *ms_update_mean = mean time of one update_R launch. */
 int b200hh_time_update_R(b200hh_t *h, int i, int reps, float *ms_update_mean);
+
+/* HLLLReduction<Z_NR<long>, FP_NR<double>>::hlll() (fplll/hlll.cpp:25-171, with size_reduction :262-354,
+ * verify_size_reduction :373-478 and lovasz_test :173-236, all default compile-time branches) over a FRESH
+ * MatHouseholder built on the handle's current basis — what hlll_reduction(ZZ_mat<long>&, delta, eta, theta, c,
+ * HM_FAST, FT_DOUBLE) runs (fplll/wrapper.cpp:789-806).  The whole loop runs on the device, one warp per lattice of
+ * the batch; the handle must have been created with keep_history (recover_R reads R_history).
+ * status[batch]: RedStatus per lattice (0 RED_SUCCESS, 10 RED_HLLL_NORM_FAILURE, 11 RED_HLLL_SR_FAILURE; 9 if the
+ * device-side iteration guard trips — the reference has no such guard).  iterations[batch] (optional): main-loop
+ * trips.  The reduced bases are read back with b200hh_get_basis. */
+int b200hh_hlll(b200hh_t *h, double delta, double eta, double theta, double c, int *status, uint64_t *iterations);
 int b200hh_sync(b200hh_t *h);
 
 #ifdef __cplusplus

@@ -295,3 +295,169 @@ void ohh_recover_R(ohh_t *m, int i)
 }
 
 void ohh_set_updated_R_false(ohh_t *m) { m->updated_R = 0; }
+
+/* ---- HLLLReduction<Z_NR<long>, FP_NR<double>>::hlll(), fplll/hlll.cpp:25-171 ------------------------------------
+ * with size_reduction (:262-354, default branch: approx = 0.1), verify_size_reduction (:373-478, default branch:
+ * the crude weak-size-reduction test) and lovasz_test (:173-236, [MSV'09] form).  compute_dR / compute_eR follow
+ * hlll.h:147-159 to the letter — eR[k] is delta * R(k,k) there (not eta * R(k,k)), and so it is here.
+ * Returns the RedStatus (defs.h:153-169): 0 success, 10 RED_HLLL_NORM_FAILURE, 11 RED_HLLL_SR_FAILURE. */
+typedef struct
+{
+  double delta, eta, theta;
+  double *dR, *eR;
+} hlll_ctx;
+
+static void h_compute_dR(ohh_t *m, hlll_ctx *c, int k)
+{
+  double f = HR(k, k);
+  f        = f * f;
+  c->dR[k] = c->delta * f;
+}
+static void h_compute_eR(ohh_t *m, hlll_ctx *c, int k) { c->eR[k] = c->delta * HR(k, k); }
+
+static void h_size_reduction(ohh_t *m, int kappa, int sr_end, int sr_start)
+{
+  int not_stop = 1, prev_not_stop = 1;
+  const double approx = 0.1;
+  ohh_update_R(m, kappa, 0);
+  m->updated_R = 0;
+  for (;;)
+  {
+    if (!ohh_size_reduce(m, kappa, sr_end, sr_start))
+      return;
+    double t       = m->norm_square_b[kappa];
+    int64_t expo0  = m->expo_norm_square_b[kappa];
+    ohh_refresh_R_bf(m, kappa);
+    double f1      = m->norm_square_b[kappa];
+    int64_t expo1  = m->expo_norm_square_b[kappa];
+    double f0      = approx * t;
+    f0             = ldexp(f0, (int)(expo0 - expo1));
+    not_stop       = (f1 <= f0);
+    ohh_update_R(m, kappa, 0);
+    if (prev_not_stop || not_stop)
+      prev_not_stop = not_stop;
+    else
+      return;
+  }
+}
+
+static int h_verify_size_reduction(ohh_t *m, hlll_ctx *c, int kappa)
+{
+  /* norm_R_row(kappa, kappa, n), householder.h:572-588 */
+  double f1 = 0.0;
+  if (m->n > kappa)
+    f1 = sqrt(dot_asc(&HR(kappa, 0), &HR(kappa, 0), kappa, m->n));
+  f1 = f1 * c->theta;
+  const int64_t expo0 = m->row_expo[kappa];
+  for (int i = 0; i < kappa; i++)
+  {
+    double f0 = fabs(HR(kappa, i));
+    double f2 = ldexp(c->eR[i], (int)(m->row_expo[i] - expo0));
+    f2        = f1 + f2;
+    if (f0 > f2)
+      return 0;
+  }
+  return 1;
+}
+
+static int h_lovasz_test(ohh_t *m, hlll_ctx *c, int k)
+{
+  double f0 = m->norm_square_b[k];
+  int64_t expo1 = m->enable_row_expo ? 2 * m->row_expo[k] : 0;
+  double f1 = 0.0;
+  if (k - 1 > 0)
+    f1 = dot_asc(&HR(k, 0), &HR(k, 0), 0, k - 1); /* norm_square_R_row(k, 0, k-1), householder.h:554-568 */
+  f1 = f0 - f1;
+  int64_t e0 = m->row_expo[k - 1];
+  f1 = ldexp(f1, (int)(expo1 - 2 * e0));
+  return c->dR[k - 1] <= f1;
+}
+
+int ohh_hlll(ohh_t *m, double delta, double eta, double theta, double cc)
+{
+  (void)cc; /* sr = 2^(-c d) is only read under HOUSEHOLDER_USE_SIZE_REDUCTION_TEST (hlll.cpp:296-312) */
+  const int d = m->d;
+  hlll_ctx c;
+  c.delta = delta, c.eta = eta, c.theta = theta;
+  c.dR = (double *)calloc(d, 8), c.eR = (double *)calloc(d, 8);
+  double *prev_R = (double *)calloc(d, 8);
+  int64_t *prev_expo = (int64_t *)calloc(d, 8);
+  int status = -1;
+  ohh_refresh_R_bf(m, 0);
+  ohh_update_R_last(m, 0);
+  h_compute_dR(m, &c, 0);
+  h_compute_eR(m, &c, 0);
+  int k = 1, k_max = 1, prev_k = -1;
+  if (d < 2)
+  {
+    status = 0;
+    goto done;
+  }
+  ohh_refresh_R_bf(m, 1);
+  for (;;)
+  {
+    h_size_reduction(m, k, k, 0);
+    if (!h_verify_size_reduction(m, &c, k))
+    {
+      status = 11;
+      break;
+    }
+    if (h_lovasz_test(m, &c, k))
+    {
+      ohh_update_R_last(m, k);
+      h_compute_dR(m, &c, k);
+      h_compute_eR(m, &c, k);
+      if (prev_k == k + 1)
+      {
+        double f0 = HR(k, k);
+        double f1 = ldexp(prev_R[k], (int)(prev_expo[k] - m->row_expo[k]));
+        if (f0 > f1)
+        {
+          status = 10;
+          break;
+        }
+      }
+      prev_k       = k;
+      prev_R[k]    = HR(k, k);
+      prev_expo[k] = m->row_expo[k];
+      k++;
+      if (k < d)
+      {
+        if (k > k_max)
+        {
+          k_max = k;
+          ohh_refresh_R_bf(m, k);
+        }
+        else
+          ohh_refresh_R(m, k);
+      }
+      else
+      {
+        status = 0;
+        break;
+      }
+    }
+    else
+    {
+      ohh_swap(m, k - 1, k);
+      prev_k = k;
+      if (k - 1 == 0)
+      {
+        ohh_refresh_R(m, 0);
+        ohh_update_R_last(m, 0);
+        h_compute_dR(m, &c, 0);
+        h_compute_eR(m, &c, 0);
+        ohh_refresh_R(m, 1);
+        k = 1;
+      }
+      else
+      {
+        k--;
+        ohh_recover_R(m, k);
+      }
+    }
+  }
+done:
+  free(c.dR), free(c.eR), free(prev_R), free(prev_expo);
+  return status;
+}

@@ -316,7 +316,8 @@ class OracleHouseholder:
                       ("ohh_size_reduce", [C.POINTER(_OHH), C.c_int, C.c_int, C.c_int]),
                       ("ohh_swap", [C.POINTER(_OHH), C.c_int, C.c_int]),
                       ("ohh_recover_R", [C.POINTER(_OHH), C.c_int]),
-                      ("ohh_set_updated_R_false", [C.POINTER(_OHH)])]:
+                      ("ohh_set_updated_R_false", [C.POINTER(_OHH)]),
+                      ("ohh_hlll", [C.POINTER(_OHH), C.c_double, C.c_double, C.c_double, C.c_double])]:
             getattr(L, f).argtypes = at
         self._p = L.ohh_create(self.d, self.n, b.ctypes.data_as(C.POINTER(C.c_int64)), flags)
 
@@ -348,6 +349,10 @@ class OracleHouseholder:
 
     def set_updated_R_false(self):
         lib().ohh_set_updated_R_false(self._p)
+
+    def hlll(self, delta=0.99, eta=0.51, theta=0.001, c=0.1):
+        """HLLLReduction::hlll() (hlll.cpp:25-171) on this object; returns the RedStatus."""
+        return int(lib().ohh_hlll(self._p, delta, eta, theta, c))
 
     def state(self):
         m = self._p.contents

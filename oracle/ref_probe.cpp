@@ -391,6 +391,13 @@ int main(int argc, char **argv)
       else
         f << Bm << endl;
     }
+    else if (c == "save_long")
+    {
+      string p;
+      is >> p;
+      ofstream f(p);
+      f << Bl << endl;
+    }
     else if (c == "tolong")
     {
       int d = Bm.get_rows(), n = Bm.get_cols();

@@ -49,9 +49,26 @@ def bkz_fixtures():
     np.savez_compressed(os.path.join(HERE, "bkz_q60.npz"), **pack)
 
 
+def hlll_fixtures():
+    # --- HLLL fixtures: the reference's HLLLReduction<long,double>::hlll (ROW_EXPO | OP_FORCE_LONG, defaults
+    # delta 0.99, eta 0.51, theta 0.001, c 0.1) on latticegen inputs that fit int64 -------------------------------
+    pack = {}
+    for tag, args in [("u40", ["u", 40, 16]), ("r60", ["r", 60, 55]), ("q40", ["q", 40, 20, 12, "b"]),
+                      ("u100", ["u", 100, 20]), ("q80", ["q", 80, 40, 16, "b"])]:
+        inp = gen(args, "hlll_%s.txt" % tag)
+        outp = os.path.join(TMP, "hlll_%s_out.txt" % tag)
+        o = O.run_ref("load %s\ntolong\nhlll_long 0.99 0.51 0.001 0.1\nsave_long %s\n" % (inp, outp), timeout=600)
+        pack[tag + "_in"] = np.array(O.read_matrix(inp), dtype=np.int64)
+        pack[tag + "_out"] = np.array(O.read_matrix(outp), dtype=np.int64)
+        pack[tag + "_status"] = np.int32(int(o.split("hlll_long status=")[1].split()[0]))
+    np.savez_compressed(os.path.join(HERE, "hlll_long.npz"), **pack)
+
+
 def main():
     if '--only-bkz' in sys.argv:
         return bkz_fixtures()
+    if '--only-hlll' in sys.argv:
+        return hlll_fixtures()
     # --- config #1 input: latticegen u 40 40 (md5 a6fe01e1...) -------------------------------
     u40 = np.array(O.read_matrix(gen(["u", 40, 40], "u40.txt")), dtype=np.int64)
     s = O.RefSession(u40)
@@ -147,6 +164,7 @@ def main():
     O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (leech_in, lo))
     np.savez_compressed(os.path.join(HERE, "leech_lll.npz"), b=np.array(O.read_matrix(lo), dtype=np.int64))
     bkz_fixtures()
+    hlll_fixtures()
     print("golden fixtures written to", HERE)
 
 

@@ -84,3 +84,43 @@ def test_full_qr_matches_gso_relation():
         for j in range(i):
             assert abs(R[i, j] / R[j, j] - s["mu"][i, j]) < 1e-9 * max(1.0, abs(s["mu"][i, j]))
             assert abs(R[i, j] * R[j, j] - s["r"][i, j]) < 1e-9 * max(1.0, abs(s["r"][i, j]))
+
+
+@pytest.mark.parametrize("tag", ["u40", "r60", "q40", "u100", "q80"])
+def test_device_hlll_equals_reference_golden(tag):
+    """b200hh_hlll (HLLLReduction::hlll, hlll.cpp:25-171, whole loop on the device) ends on the basis the reference's
+    HLLLReduction<long,double> produced; a batch of copies plus one differently-scaled lattice checks lattices of a
+    batch do not interact."""
+    from fplll_b200.householder import hlll_reduction
+    g = H.gold("hlll_long.npz")
+    b_in = g[tag + "_in"]
+    out, st = hlll_reduction(b_in)
+    assert st == int(g[tag + "_status"]) == 0
+    assert np.array_equal(out, g[tag + "_out"])
+    batch = np.stack([b_in, 3 * b_in, b_in])
+    outs, sts = hlll_reduction(batch)
+    assert list(sts) == [0, 0, 0]
+    assert np.array_equal(outs[0], g[tag + "_out"]) and np.array_equal(outs[2], g[tag + "_out"])
+    mo = O.OracleHouseholder(3 * b_in)
+    assert mo.hlll() == 0 and np.array_equal(outs[1], mo.state()["b"])
+
+
+@pytest.mark.parametrize("seed,d,n,bits,batch", [(11, 30, 30, 25, 4), (12, 50, 55, 12, 3), (13, 70, 70, 40, 2),
+                                                 (14, 1, 5, 10, 2), (15, 2, 2, 30, 2)])
+def test_device_hlll_equals_oracle_random(seed, d, n, bits, batch):
+    from fplll_b200.householder import hlll_reduction
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-(1 << bits), 1 << bits, size=(batch, d, n), dtype=np.int64)
+    outs, sts = hlll_reduction(b)
+    for l in range(batch):
+        mo = O.OracleHouseholder(b[l])
+        assert mo.hlll() == sts[l], "lattice %d status" % l
+        assert np.array_equal(outs[l], mo.state()["b"]), "lattice %d basis" % l
+
+
+def test_device_hlll_needs_history():
+    from fplll_b200.householder import MatHouseholder
+    from fplll_b200 import B200Error
+    m = MatHouseholder(H.gold("hlll_long.npz")["u40_in"], 5, keep_history=False)
+    with pytest.raises(B200Error):
+        m.hlll()

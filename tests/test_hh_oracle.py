@@ -85,3 +85,33 @@ def test_householder_relation_with_gso():
         for j in range(i):
             assert abs(R[i, j] / R[j, j] - s["mu"][i, j]) < 1e-9 * max(1.0, abs(s["mu"][i, j]))
             assert abs(R[i, j] * R[j, j] - s["r"][i, j]) < 1e-9 * max(1.0, abs(s["r"][i, j]))
+
+
+HLLL_TAGS = ["u40", "r60", "q40", "u100", "q80"]
+
+
+@pytest.mark.parametrize("tag", HLLL_TAGS)
+def test_oracle_hlll_equals_reference_golden(tag):
+    """ohh_hlll (the restated HLLLReduction::hlll, hlll.cpp:25-171) ends on the basis the reference's own
+    HLLLReduction<long,double> produced (tests/golden/hlll_long.npz, made by make_golden.py --only-hlll)."""
+    g = H.gold("hlll_long.npz")
+    m = O.OracleHouseholder(g[tag + "_in"])
+    st = m.hlll(0.99, 0.51, 0.001, 0.1)
+    assert st == int(g[tag + "_status"]) == 0
+    assert np.array_equal(m.state()["b"], g[tag + "_out"])
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,d,bits", [(5, 30, 25), (6, 50, 12), (7, 70, 40)])
+def test_oracle_hlll_live_vs_reference(seed, d, bits):
+    """same, on seeded random bases, against the reference run live (status and output basis)."""
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-(1 << bits), 1 << bits, size=(d, d), dtype=np.int64)
+    tmp = O.tempfile.mkdtemp(prefix="hlll_")
+    pin, pout = os.path.join(tmp, "in.txt"), os.path.join(tmp, "out.txt")
+    O.write_matrix(pin, b)
+    o = O.run_ref("load %s\ntolong\nhlll_long 0.99 0.51 0.001 0.1\nsave_long %s\n" % (pin, pout))
+    rst = int(o.split("hlll_long status=")[1].split()[0])
+    m = O.OracleHouseholder(b)
+    assert m.hlll() == rst
+    assert np.array_equal(m.state()["b"], np.array(O.read_matrix(pout), dtype=np.int64))
