@@ -27,17 +27,30 @@ def _stale(out, srcs):
 
 
 def build_all(force=False, verbose=False):
-    os.makedirs(LIBDIR, exist_ok=True)
+    """Each .cu is compiled ONCE to an object (the four translation units in parallel; gso_api.cu alone takes minutes:
+    three Babai widths x two LLL kernels, fully unrolled), then every library is linked from the objects it needs."""
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    units = sorted({u for srcs in TARGETS.values() for u in srcs})
+
+    def compile_unit(u):
+        src, obj = os.path.join(CSRC, u), os.path.join(objdir, u[:-3] + ".o")
+        if force or _stale(obj, [src]):
+            subprocess.check_call(["nvcc", "--split-compile", "0"] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+        objs = dict(zip(units, ex.map(compile_unit, units)))
     built = []
     for name, srcs in TARGETS.items():
-        paths = [os.path.join(CSRC, s) for s in srcs]
-        if not all(os.path.exists(p) for p in paths):
-            continue
         out = os.path.join(LIBDIR, name)
-        if force or _stale(out, paths):
-            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + paths
-            if name == "libb200enum.so":
-                cmd += ["-lnccl"] if os.environ.get("B200_WITH_NCCL") else []
+        deps = [objs[u] for u in srcs]
+        if force or not os.path.exists(out) or any(os.path.getmtime(o) > os.path.getmtime(out) for o in deps):
+            cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + deps
+            if name == "libb200enum.so" and os.environ.get("B200_WITH_NCCL"):
+                cmd += ["-lnccl"]
             subprocess.check_call(cmd)
         built.append(out)
     return built

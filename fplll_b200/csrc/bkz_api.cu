@@ -87,13 +87,14 @@ public:
   {
     const double t0 = now_s();
     int status      = 0;
-    long stats[8]   = {0, 0, 0, 0, 0, 0, 0, 0};
+    long stats[12]  = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     GCK(b200gso_lll_range(g, lll_delta, 0.51, kmin, kstart, kend, 0, &status, stats));
     const double dt = now_s() - t0;
     st->sec_lll += dt;
     st->lll_calls++;
 #ifdef B200_LLL_PROFILE
-    prof_cyc[0] += stats[4], prof_cyc[1] += stats[5], prof_cyc[2] += stats[6], prof_cyc[3] += stats[7];
+    for (int q = 0; q < 8; q++)
+      prof_cyc[q] += stats[4 + q];
     prof_lll_sec += dt;
     prof_swaps += stats[0], prof_iters += stats[3];
 #endif
@@ -108,6 +109,7 @@ public:
     int status      = 0;
     GCK(b200gso_size_reduction(g, 0.51, kmin, kend, sr_start, &status));
     st->sec_lll += now_s() - t0;
+    prof_sr_sec += now_s() - t0;
     st->sizered_calls++;
     if (status != 0)
       throw RedFailure{status};  // bkz.cpp:289-292
@@ -120,8 +122,8 @@ public:
     st->sec_get += now_s() - t0;
     st->get_calls++;
   }
-  long long prof_cyc[4] = {0, 0, 0, 0};
-  double prof_lll_sec    = 0;
+  long long prof_cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_lll_sec = 0, prof_sr_sec = 0;
   long prof_swaps = 0, prof_iters = 0;
   // recorded GSO calls, flushed as one kernel launch (b200gso_apply_ops)
   std::vector<b200gso_op> ops;
@@ -649,6 +651,10 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
                     "lovasz %.3g, move_row+set_r %.3g; swaps %ld, babai iterations %ld\n",
             drv.prof_lll_sec, (double)drv.prof_cyc[0], (double)drv.prof_cyc[1], (double)drv.prof_cyc[2],
             (double)drv.prof_cyc[3], drv.prof_swaps, drv.prof_iters);
+    fprintf(stderr, "  inside babai-rest: gather/scan %.3g, back-substitution %.3g, compaction+integer rows %.3g, row_op_end "
+                    "%.3g cycles; size_reduction calls %.1f s wall\n",
+            (double)drv.prof_cyc[4], (double)drv.prof_cyc[5], (double)drv.prof_cyc[6], (double)drv.prof_cyc[7],
+            drv.prof_sr_sec);
 #endif
     stats->sec_other = stats->sec_total - stats->sec_enum - stats->sec_lll;
     if (stats->status == 0 || stats->status == B200_RED_BKZ_LOOPS_LIMIT || stats->status == B200_RED_BKZ_TIME_LIMIT)

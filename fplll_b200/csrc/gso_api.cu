@@ -375,6 +375,74 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
   }
 }
 
+// Single-lattice regime (BKZ): one CTA of CTA_WARPS warps per lattice, warp 0 runs the LLL / size-reduction control
+// flow and shares the O(kappa d) pieces of every Babai iteration with the other warps (gso_cta.cuh).
+// mode 0: lll(kmin, kstart, kend, sr_start); mode 1: size_reduction(kmin, kend, sr_start).
+__host__ __device__ inline size_t cta_smem_doubles(int d, int n)
+{
+  const size_t per = WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1) + ((((MetaCache::ints(d) + 1) >> 1) + 1) & ~(size_t)1);
+  return per + ((sizeof(CoopShared) + 15) / 16) * 2 + (size_t)((d + 32 + 1) & ~1);
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(CTA_WARPS * 32)
+    k_lll_cta(Batch S, int mode, double delta, double eta, int kmin, int kstart, int kend, int sr_start, int *status,
+              long *stats)
+{
+  extern __shared__ __align__(16) double smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, l = blockIdx.x;
+  const size_t base = WarpSmem::doubles(S.d, S.n);
+  const size_t lovn = (size_t)((S.d + 2 + 1) & ~1);
+  const size_t per  = base + lovn + ((((MetaCache::ints(S.d) + 1) >> 1) + 1) & ~(size_t)1);
+  CoopShared *C     = reinterpret_cast<CoopShared *>(smem + per);
+  double *bm        = smem + per + ((sizeof(CoopShared) + 15) / 16) * 2;
+  if (w != 0)
+  {
+    coop_helper_loop(*C, w, lane);
+    return;
+  }
+  View v = S.view(l);
+  WarpSmem s;
+  s.carve(smem, S.d, S.n, true);
+  double *lov = smem + base;
+  MetaCache mc;
+  mc.load(v, (int *)(lov + lovn), lane);
+  if (lane == 0)
+  {
+    C->v = v;
+    C->s = s;
+    C->bm = bm;
+    C->cmd = COOP_EXIT, C->flag = 1;
+  }
+  __syncwarp();
+  LLLStats st;
+  st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
+  int r;
+  if (mode == 0)
+    r = warp_lll<MAXQ, true>(v, s, lov, delta, eta, kmin, kstart, kend, sr_start, lane, st, C);
+  else
+    r = warp_size_reduction<MAXQ, true>(v, s, kmin, kend, sr_start, eta, lane, st.babai_iters, C);
+  coop_post(C, COOP_EXIT, 0, 0, 0, lane);
+  mc.store(v, lane);
+  if (lane == 0)
+  {
+    status[l] = r;
+    if (stats)
+    {
+      stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
+      stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
+#ifdef B200_LLL_PROFILE
+      if (mode == 0)
+      {
+        long *px = stats + 4 * S.B;
+        px[0] = st.cyc_update, px[1] = st.cyc_babai, px[2] = st.cyc_lovasz, px[3] = st.cyc_move;
+        px[4] = st.cyc_gather, px[5] = st.cyc_backsub, px[6] = st.cyc_igemv, px[7] = st.cyc_ropend;
+      }
+#endif
+    }
+  }
+}
+
 template <int MAXQ>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     k_size_reduction(Batch S, double eta, int kmin, int kend, int sr_start, int *status)
@@ -637,6 +705,12 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
                        (const void *)k_size_reduction<16>, (const void *)k_apply_ops};
   for (const void *f : fns)
     CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  {
+    const int sm = (int)(cta_smem_doubles(d, n) * sizeof(double));
+    CK(cudaFuncSetAttribute((const void *)k_lll_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute((const void *)k_lll_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute((const void *)k_lll_cta<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  }
   CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
   CK(cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream));
   CK(cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream));
@@ -929,6 +1003,33 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
   int *d_st     = h->d_ok;
   long *d_stats = stats ? h->d_stats : nullptr;  // preallocated: stream-ordered allocation would hand its memory back
                                                  // to the driver at every synchronisation and cost milliseconds
+  // few lattices (BKZ works on one): a whole CTA per lattice (k_lll_cta); many: one warp per lattice, the batch hides
+  // the latencies.  B200_LLL_CTA=0 forces the one-warp kernels, B200_LLL_CTA_MAX moves the switch-over.
+  const int cta_on  = getenv("B200_LLL_CTA") ? atoi(getenv("B200_LLL_CTA")) : 1;
+  const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
+  if (cta_on && S.B <= cta_max && S.d > 32)
+  {
+    const size_t sm = cta_smem_doubles(S.d, S.n) * sizeof(double);
+    long *d_stats_c = (stats && mode == 0) ? h->d_stats : nullptr;
+    if (S.d <= 128)
+      k_lll_cta<4><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+    else if (S.d <= 256)
+      k_lll_cta<8><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+    else
+      k_lll_cta<16><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+    CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
+    if (stats)
+    {
+#ifdef B200_LLL_PROFILE
+      CK(cudaMemcpyAsync(stats, h->d_stats, sizeof(long) * (4 * S.B + 8), cudaMemcpyDeviceToHost, h->stream));
+#else
+      CK(cudaMemcpyAsync(stats, h->d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
+#endif
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+  }
   const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
 #define LLL_LAUNCH(Q)                                                                                          \
   do                                                                                                           \

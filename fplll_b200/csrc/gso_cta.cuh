@@ -1,0 +1,389 @@
+// gso_cta.cuh — CTA-cooperative pieces of the device LLL for the single-lattice (BKZ) regime.
+//
+// With one warp per lattice (gso_lll.cuh) a Babai iteration on a dim-200 basis costs ~185 us: every load is an exposed
+// L2 round trip and every dependent instruction an exposed pipeline latency (profiles/r1_lll_phase_breakdown.txt,
+// ncu: 5.4 of 10.6 cycles per issued instruction are long-scoreboard stalls, IPC 0.09).  A batch hides that behind
+// other lattices; BKZ on ONE lattice cannot.  Here one CTA of CTA_WARPS warps serves one lattice: warp 0 (the master)
+// runs the LLL control flow of gso_lll.cuh unchanged, and the three O(kappa * d) pieces of an iteration are executed by
+// all warps as SPMD "cooperative operations", one 32-column panel per warp:
+//
+//   UPDATE   update_gso_row(i, last_j): Gram entries of different panels in parallel, then the forward substitution
+//            as a WAVEFRONT over panels — panel p applies the tiles (p, q) in ascending q as soon as panel q's
+//            r(i, .) are final, so the critical path is P (triangle + one tile) instead of P^2/2 tiles.
+//   BACKSUB  Babai's back-substitution (lll.cpp:202-214) as the mirrored wavefront, panels descending.
+//   IGEMV    the fused integer row update b_kappa += sum_j (-X_j 2^e_j) b_j, columns split over the warps.
+//
+// Every output element is still produced by exactly the reference's sequence of correctly rounded operations (the
+// per-lane chains are the ones of gso_warp.cuh / gso_lll.cuh, cut at panel boundaries), so results are bit-identical to
+// the one-warp kernels — tests/test_gso_gpu.py runs both against the same reference trajectories.
+//
+// Synchronisation: named barrier 1 dispatches a command (master posts it in shared memory, all warps arrive), named
+// barrier 2 separates the steps inside an operation (all warps execute the same operation with warp-uniform control
+// flow).  No spin-waits.
+#pragma once
+#include "gso_warp.cuh"
+
+namespace b200 {
+
+constexpr int CTA_WARPS = 8;
+constexpr int CTA_OWN   = 2;  // panels a warp can own: 16 panels = d <= 512
+
+enum { COOP_EXIT = 0, COOP_UPDATE = 1, COOP_BACKSUB = 2, COOP_IGEMV = 3 };
+
+struct CoopShared
+{
+  View v;      // the master's view (its metadata pointers point into the master's shared-memory cache)
+  WarpSmem s;  // the master's scratch rows (vb, rrow, murow, aux, xs)
+  double *bm;  // babai_mu row handed to BACKSUB
+  int cmd, a0, a1, a2;
+  int flag;
+};
+
+__device__ inline void cta_bar(int id)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(CTA_WARPS * 32) : "memory");
+}
+
+// master: publish a command and release the helpers (they wait in barrier 1)
+__device__ inline void coop_post(CoopShared *C, int cmd, int a0, int a1, int a2, int lane)
+{
+  __syncwarp();
+  if (lane == 0)
+  {
+    C->cmd = cmd;
+    C->a0 = a0, C->a1 = a1, C->a2 = a2;
+  }
+  __syncwarp();
+  cta_bar(1);
+}
+
+// ---- UPDATE ---------------------------------------------------------------------------------------------------------
+// update_gso_row(i, last_j) for a row that is already discovered and has valid[i] <= last_j (the master checks both).
+// Same arithmetic as warp_update_gso_row: lane l of panel p owns column j = 32p + l,
+//   acc_j = g(i,j); acc_j -= mu(j,k) r(i,k) for k = 0 .. j-1 ascending.
+__device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int lane)
+{
+  const View &v = C.v;
+  WarpSmem &s   = C.s;
+  const int tid = threadIdx.x;
+  const int j0  = max(0, v.valid[i]);
+  const int ncols = v.meta[M_NKC], n = v.n;
+  double *gfrow = v.gf + tri_off(i), *rrow_g = v.r + tri_off(i);
+  const int jl = min(last_j, i - 1);  // last off-diagonal column to produce
+  const int p0 = j0 >> 5;
+  const int pl = (jl >= j0) ? (jl >> 5) : p0 - 1;  // panels p0..pl carry work (none if only the diagonal is asked for)
+
+  if (w == 0)
+  {
+    int anyn = 0;
+    for (int j = j0 + lane; j <= last_j; j += 32)
+      anyn |= (gfrow[j] != gfrow[j]);
+    if (__any_sync(FULL, anyn))
+      warp_stage_bf_row(v, i, ncols, s.vb, lane);
+    if (lane == 0)
+      C.flag = 1;
+  }
+  for (int k = tid; k < j0; k += CTA_WARPS * 32)
+    s.rrow[k] = rrow_g[k];
+  cta_bar(2);
+
+  // Gram entries + the part of every chain that only needs the already-valid r(i, k), k < 32 p0
+  double acc[CTA_OWN];
+  bool act[CTA_OWN];
+#pragma unroll
+  for (int u = 0; u < CTA_OWN; u++)
+  {
+    const int p = p0 + w + CTA_WARPS * u;
+    const int j = 32 * p + lane;
+    act[u]      = (p <= pl) && (j >= j0) && (j <= jl);
+    double a    = 0.0;
+    if (act[u])
+    {
+      double g = gfrow[j];
+      if (g != g)
+      {
+        g        = lane_dot(v.bf + bf_off(j, 0, n), s.vb, ncols);
+        gfrow[j] = g;
+      }
+      a = lane_chain<true>(g, v.mu + mu_panel_base(p) + lane, s.rrow, 0, 32 * p0);
+    }
+    else if (p <= pl && j < j0)
+      a = s.rrow[j];  // already-valid r(i,j): only broadcast in the triangle below
+    acc[u] = a;
+  }
+
+  bool ok = true;
+  for (int sp = p0; sp <= pl; ++sp)
+  {
+    const int ow = (sp - p0) % CTA_WARPS, ou = (sp - p0) / CTA_WARPS;
+    if (ow == w)
+    {
+      // triangular part of panel sp: column 32 sp + t is final in lane t once steps 0..t-1 are applied
+#pragma unroll
+      for (int u = 0; u < CTA_OWN; u++)
+        if (u == ou)
+        {
+          const int j        = 32 * sp + lane;
+          const bool a_      = act[u];
+          double a           = acc[u];
+          const double *tile = v.mu + mu_panel_base(sp) + lane + (size_t)(32 * sp) * 32;
+          double rd          = 1.0;
+          double m[8], mn[8];
+#pragma unroll
+          for (int x = 0; x < 8; x++)
+            m[x] = (a_ && lane >= x) ? tile[(size_t)x * 32] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+          {
+            if (q < 3)
+            {
+#pragma unroll
+              for (int x = 0; x < 8; x++)
+                mn[x] = (a_ && lane >= 8 * (q + 1) + x) ? tile[(size_t)(8 * (q + 1) + x) * 32] : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+            {
+              const int t = 8 * q + x;
+              if (lane == t)
+                rd = m[x];
+              if (t < 31)
+              {
+                const double rk = __shfl_sync(FULL, a, t);
+                if (a_ && lane > t)
+                  a = __dsub_rn(a, __dmul_rn(m[x], rk));
+              }
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+              m[x] = mn[x];
+          }
+          if (a_)
+          {
+            rrow_g[j]          = a;
+            s.rrow[j]          = a;
+            const double mm    = __ddiv_rn(a, rd);
+            v.mu[mu_off(i, j)] = mm;
+            s.murow[j]         = mm;
+            if (!isfinite(mm))
+              ok = false;
+          }
+          acc[u] = a;
+        }
+    }
+    cta_bar(2);
+    // everybody below: apply the tile (p, sp) now that r(i, 32 sp .. 32 sp + 31) are final
+#pragma unroll
+    for (int u = 0; u < CTA_OWN; u++)
+    {
+      const int p = p0 + w + CTA_WARPS * u;
+      if (p > sp && act[u])
+        acc[u] = lane_chain<true>(acc[u], v.mu + mu_panel_base(p) + lane, s.rrow, 32 * sp, 32 * sp + 32);
+    }
+  }
+  if (!ok)
+    C.flag = 0;
+  cta_bar(2);
+  if (!C.flag)
+    return false;
+
+  if (last_j >= i)
+  {
+    // diagonal r(i,i) = g(i,i) - sum_{k<i} mu(i,k) r(i,k): products in parallel, one ordered subtraction chain
+    for (int k = tid; k < min(j0, i); k += CTA_WARPS * 32)
+      s.murow[k] = v.mu[mu_off(i, k)];
+    cta_bar(2);
+    for (int k = tid; k < i; k += CTA_WARPS * 32)
+      s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
+    cta_bar(2);
+    if (tid == 0)
+    {
+      double g = gfrow[i];
+      if (g != g)
+      {
+        g = __dmul_rn(s.vb[0], s.vb[0]);
+        for (int c = 1; c < ncols; c++)
+          g = __dadd_rn(g, __dmul_rn(s.vb[c], s.vb[c]));
+        gfrow[i] = g;
+      }
+      double a = g;
+      for (int k = 0; k < i; k++)
+        a = __dsub_rn(a, s.aux[k]);
+      rrow_g[i]          = a;
+      v.mu[mu_off(i, i)] = a;  // diagonal mirror
+    }
+  }
+  if (tid == 0)
+    v.valid[i] = last_j + 1;
+  cta_bar(2);
+  return true;
+}
+
+// ---- BACKSUB --------------------------------------------------------------------------------------------------------
+// X_j = rnd_we(babai_mu[j]); babai_mu[k] -= X_j * mu(j,k) for k < j, j descending (lll.cpp:202-214).  C.bm holds
+// babai_mu (columns < sr_end); the X_j land in s.xs[j], the per-panel masks of the non-zero ones in xmask[].
+__device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, int w, int lane)
+{
+  const View &v = C.v;
+  WarpSmem &s   = C.s;
+  const int ek  = v.row_expo[kappa];
+  unsigned *xmask = (unsigned *)(s.xs + ((v.d + 1) & ~1));
+  const int p_hi = (sr_end - 1) >> 5, p_lo = sr_start >> 5;
+  // panel q is owned by warp (p_hi - q) % CTA_WARPS, slot (p_hi - q) / CTA_WARPS
+  double val[CTA_OWN];
+#pragma unroll
+  for (int u = 0; u < CTA_OWN; u++)
+  {
+    const int q = p_hi - w - CTA_WARPS * u;
+    const int k = 32 * q + lane;
+    val[u]      = (q >= p_lo && k < sr_end) ? C.bm[k] : 0.0;
+  }
+  for (int p = p_hi; p >= p_lo; --p)
+  {
+    const int ow = (p_hi - p) % CTA_WARPS, ou = (p_hi - p) / CTA_WARPS;
+    if (ow == w)
+    {
+#pragma unroll
+      for (int u = 0; u < CTA_OWN; u++)
+        if (u == ou)
+        {
+          double a              = val[u];
+          const int kcol        = 32 * p + lane;
+          const double *tilecol = v.mu + mu_panel_base(p) + (size_t)kcol * 32;  // mu(32p+t, kcol) at [t]
+          unsigned nzmask       = 0;
+          double tc[32];
+#pragma unroll
+          for (int t = 0; t < 32; t++)
+            tc[t] = (t > lane && 32 * p + t < sr_end) ? tilecol[t] : 0.0;
+#pragma unroll
+          for (int t = 31; t >= 0; --t)
+          {
+            const int j = 32 * p + t;
+            if (j >= sr_end || j < sr_start)
+              continue;
+            const double bj = __shfl_sync(FULL, a, t);
+            const long de   = v.row_expo_en ? (long)(ek - v.row_expo[j]) : 0;
+            const double X  = rnd_we(bj, de);
+            if (X == 0.0)
+              continue;
+            nzmask |= 1u << t;
+            if (lane == 0)
+              s.xs[j] = X;
+            if (lane < t && kcol >= sr_start)
+              a = __dsub_rn(a, __dmul_rn(X, tc[t]));
+          }
+          if (lane == 0)
+            xmask[p] = nzmask;
+          val[u] = a;
+        }
+    }
+    cta_bar(2);
+    const unsigned nzmask = xmask[p];
+    if (nzmask)
+    {
+#pragma unroll
+      for (int u = 0; u < CTA_OWN; u++)
+      {
+        const int q = p_hi - w - CTA_WARPS * u;
+        const int k = 32 * q + lane;
+        if (q < p && q >= p_lo && k >= sr_start)
+        {
+          const double *col = v.mu + mu_panel_base(p) + (size_t)k * 32;
+          double a          = val[u];
+          double cv[32];  // mu(32p + t, k), t = 0..31: 32 independent loads in flight
+#pragma unroll
+          for (int t = 0; t < 32; t++)
+            cv[t] = ((nzmask >> t) & 1u) ? col[t] : 0.0;
+#pragma unroll
+          for (int t = 31; t >= 0; --t)  // rows with X != 0 only, still in descending order
+            if ((nzmask >> t) & 1u)
+              a = __dsub_rn(a, __dmul_rn(s.xs[32 * p + t], cv[t]));
+          val[u] = a;
+        }
+      }
+    }
+  }
+}
+
+// ---- IGEMV ----------------------------------------------------------------------------------------------------------
+// b_kappa += sum_t lx_t * 2^e_t * b_{row_t} over the nnz compacted rows (lx in s.aux[t], (e << 32 | row) in s.murow[t]):
+// row_addmul_we (gso.cpp:236-262) fused over j; int64 arithmetic wraps, so the order of the additions is immaterial.
+// Warp w takes the column groups w, w + CTA_WARPS, ... of 32 columns.
+__device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int lane)
+{
+  const View &v = C.v;
+  WarpSmem &s   = C.s;
+  const int nc  = v.meta[M_NKC];
+  unsigned long long *bk = (unsigned long long *)(v.b + (size_t)kappa * v.ldb);
+  for (int c0 = 32 * w; c0 < nc; c0 += 32 * CTA_WARPS)
+  {
+    const int c = c0 + lane;
+    unsigned long long acc = (c < nc) ? bk[c] : 0ull;
+    for (int t0 = 0; t0 < nnz; t0 += 16)
+    {
+      unsigned long long bv[16], lxv[16];
+      int ev[16];
+#pragma unroll
+      for (int x = 0; x < 16; x++)
+      {
+        const int t = t0 + x;
+        bv[x] = 0ull, lxv[x] = 0ull, ev[x] = 0;
+        if (t < nnz)
+        {
+          lxv[x]             = (unsigned long long)__double_as_longlong(s.aux[t]);
+          const long long pk = __double_as_longlong(s.murow[t]);
+          ev[x]              = (int)(pk >> 32);
+          const unsigned long long *src = (const unsigned long long *)(v.b + (size_t)(int)(pk & 0xffffffffll) * v.ldb);
+          if (c < nc)
+            bv[x] = src[c];
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 16; x++)
+      {
+        const unsigned long long tt = bv[x] * lxv[x];
+        acc += (ev[x] >= 64 ? 0ull : (tt << ev[x]));
+      }
+    }
+    if (c < nc)
+      bk[c] = acc;
+  }
+  cta_bar(2);
+}
+
+// helper warps: wait for commands until the master says EXIT
+__device__ inline void coop_helper_loop(CoopShared &C, int w, int lane)
+{
+  for (;;)
+  {
+    cta_bar(1);
+    const int cmd = C.cmd, a0 = C.a0, a1 = C.a1, a2 = C.a2;
+    if (cmd == COOP_EXIT)
+      break;
+    if (cmd == COOP_UPDATE)
+      (void)cta_update_gso_row(C, a0, a1, w, lane);
+    else if (cmd == COOP_BACKSUB)
+      cta_backsub(C, a0, a1, a2, w, lane);
+    else if (cmd == COOP_IGEMV)
+      cta_igemv(C, a0, a1, w, lane);
+  }
+}
+
+// master side of update_gso_row: the reference's early exits, then the cooperative operation
+template <bool COOP>
+__device__ inline bool lll_update_gso_row(const View &v, int i, int last_j, WarpSmem &s, int lane, CoopShared *C)
+{
+  if (!COOP)
+    return warp_update_gso_row(v, i, last_j, s, lane);
+  if (i >= v.meta[M_NKR])
+    warp_discover_row(v, lane);
+  const int j0 = max(0, v.valid[i]);
+  if (j0 > last_j)
+    return true;
+  if (i < 32)
+    return warp_update_gso_row(v, i, last_j, s, lane);  // a single panel: nothing to share
+  coop_post(C, COOP_UPDATE, i, last_j, 0, lane);
+  return cta_update_gso_row(*C, i, last_j, 0, lane);
+}
+
+}  // namespace b200

@@ -5,6 +5,7 @@
 // the CPU spends ~1 us per such call, less than one kernel launch).  Control flow is warp-uniform; every
 // floating-point chain keeps the reference's operation order so the basis trajectory is the reference's.
 #pragma once
+#include "gso_cta.cuh"
 #include "gso_warp.cuh"
 
 namespace b200 {
@@ -18,33 +19,35 @@ struct LLLStats
   // device-clock breakdown (SM cycles of the owning warp): update_gso_row, rest of babai (scan, back-substitution,
   // integer row operations, row_op_end), Lovasz test, move_row
   long long cyc_update, cyc_babai, cyc_lovasz, cyc_move;
+  long long cyc_gather, cyc_backsub, cyc_igemv, cyc_ropend;  // inside cyc_babai
 };
 
 #ifdef B200_LLL_PROFILE
-#define LLL_T0() const long long t0_ = clock64()
-#define LLL_ACC(field) (field) += clock64() - t0_
+#define LLL_PT(var) const long long var = clock64()
+#define LLL_PACC(field, t0) \
+  do                        \
+  {                         \
+    if (pst)                \
+      pst->field += clock64() - (t0); \
+  } while (0)
 #else
-#define LLL_T0()
-#define LLL_ACC(field)
+#define LLL_PT(var)
+#define LLL_PACC(field, t0)
 #endif
 
 // LLLReduction::babai(kappa, size_reduction_end, size_reduction_start), lll.cpp:166-224.
 // MAXQ*32 >= d.  Returns RED_SUCCESS or the failing status (warp-uniform).
-template <int MAXQ>
+template <int MAXQ, bool COOP = false>
 __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int sr_start, double eta,
-                                 int lane, long &iters, long long *cyc_update = nullptr)
+                                 int lane, long &iters, LLLStats *pst = nullptr, CoopShared *C = nullptr)
 {
   long max_expo = LONG_MAX;
   for (int iter = 0;; iter++)
   {
-#ifdef B200_LLL_PROFILE
-    const long long tu_ = clock64();
-#endif
-    const bool upd_ok = warp_update_gso_row(v, kappa, sr_end - 1, s, lane);
-#ifdef B200_LLL_PROFILE
-    if (cyc_update)
-      *cyc_update += clock64() - tu_;
-#endif
+    LLL_PT(tu_);
+    const bool upd_ok = lll_update_gso_row<COOP>(v, kappa, sr_end - 1, s, lane, C);
+    LLL_PACC(cyc_update, tu_);
+    LLL_PT(tg_);
     if (!upd_ok)
       return RED_GSO_FAILURE;
     // gather row kappa of mu (stride-32 in the panel layout) + exponent differences
@@ -83,8 +86,23 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
     if (lane < MAXQ)
       xmask[lane] = 0;
     __syncwarp();
+    LLL_PACC(cyc_gather, tg_);
+    LLL_PT(tb_);
     // back-substitution, j descending (lll.cpp:202-214): X_j = rnd_we(babai_mu[j]); babai_mu[k] -= X_j*mu(j,k), k<j
-    for (int p = (sr_end - 1) >> 5; p >= (sr_start >> 5); --p)
+    const bool coop_bs = COOP && sr_end > 32;  // more than one panel: wavefront over the CTA's warps (gso_cta.cuh)
+    if (coop_bs)
+    {
+#pragma unroll
+      for (int q = 0; q < MAXQ; q++)
+      {
+        const int k = 32 * q + lane;
+        if (k < sr_end)
+          C->bm[k] = bm[q];
+      }
+      coop_post(C, COOP_BACKSUB, kappa, sr_end, sr_start, lane);
+      cta_backsub(*C, kappa, sr_end, sr_start, 0, lane);
+    }
+    for (int p = coop_bs ? -1 : ((sr_end - 1) >> 5); p >= (sr_start >> 5); --p)
     {
       // in-panel triangle: lane l owns column k = 32p+l
       double val = 0.0;
@@ -146,6 +164,8 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
       }
     }
     __syncwarp();
+    LLL_PACC(cyc_backsub, tb_);
+    LLL_PT(ti_);
     // integer row operations b_kappa += (-X_j) * 2^expo_j * b_j, fused over j (row_addmul_we, gso.cpp:236-262).
     // Integer additions commute exactly (mod 2^64), so one pass over the columns applies all j.  Only the rows with
     // X_j != 0 are visited (typically a handful): compact them first — lx -> aux[t], shift -> murow[t], row -> xs'[t].
@@ -169,7 +189,12 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
       }
     }
     __syncwarp();
-    if (nnz)
+    if (COOP && nnz)
+    {
+      coop_post(C, COOP_IGEMV, kappa, nnz, 0, lane);
+      cta_igemv(*C, kappa, nnz, 0, lane);
+    }
+    else if (nnz)
     {
       // lane l owns columns l, l+32, ... of a group of up to 8*32 columns: 4 source rows x 8 column chunks = 32 loads in
       // flight per round (the source rows are contiguous, every load is a 256-byte coalesced line)
@@ -227,7 +252,10 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
       }
     }
     __syncwarp();
+    LLL_PACC(cyc_igemv, ti_);
+    LLL_PT(tr_);
     warp_row_op_end(v, kappa, kappa + 1, lane);
+    LLL_PACC(cyc_ropend, tr_);
   }
   return RED_SUCCESS;
 }
@@ -288,9 +316,9 @@ __device__ inline double warp_get_gram_diag(const View &v, WarpSmem &s, int i, i
 }
 
 // LLLReduction::size_reduction(kappa_min, kappa_end, size_reduction_start), lll.h:106-122
-template <int MAXQ>
+template <int MAXQ, bool COOP = false>
 __device__ inline int warp_size_reduction(const View &v, WarpSmem &s, int kappa_min, int kappa_end, int sr_start,
-                                          double eta, int lane, long &iters)
+                                          double eta, int lane, long &iters, CoopShared *C = nullptr)
 {
   // Rows below the clean prefix are size-reduced with a valid GSO and untouched since: on them the reference's loop
   // body (babai finds nothing to reduce, update_gso_row finds the row valid) changes no state, so start after them.
@@ -302,11 +330,11 @@ __device__ inline int warp_size_reduction(const View &v, WarpSmem &s, int kappa_
   {
     if (k > 0)
     {
-      const int st = warp_babai<MAXQ>(v, s, k, k, sr_start, eta, lane, iters);
+      const int st = warp_babai<MAXQ, COOP>(v, s, k, k, sr_start, eta, lane, iters, nullptr, C);
       if (st != RED_SUCCESS)
         return st;
     }
-    if (!warp_update_gso_row(v, k, k, s, lane))
+    if (!lll_update_gso_row<COOP>(v, k, k, s, lane, C))
       return RED_GSO_FAILURE;  // the reference returns false here without touching status (lll.h:118-119)
   }
   if (sr_start == 0 && kappa_min <= clean && lane == 0)
@@ -329,14 +357,16 @@ __device__ inline int warp_size_reduction(const View &v, WarpSmem &s, int kappa_
 
 // LLLReduction::lll(kappa_min, kappa_start, kappa_end, size_reduction_start), lll.cpp:44-164; LLL_DEFAULT flags
 // (no siegel, no early reduction, not verbose).  lov = shared array of d+1 doubles.
-template <int MAXQ>
+template <int MAXQ, bool COOP = false>
 __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double delta, double eta, int kappa_min,
-                               int kappa_start, int kappa_end, int sr_start, int lane, LLLStats &st)
+                               int kappa_start, int kappa_end, int sr_start, int lane, LLLStats &st,
+                               CoopShared *C = nullptr)
 {
   const int d = kappa_end - kappa_min;
   int kappa = kappa_start + 1, zeros = 0;
   st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
   st.cyc_update = st.cyc_babai = st.cyc_lovasz = st.cyc_move = 0;
+  st.cyc_gather = st.cyc_backsub = st.cyc_igemv = st.cyc_ropend = 0;
   const double swap_threshold = delta;
   // Clean prefix: rows [0, c) are (delta, eta)-LLL-reduced with a valid GSO and untouched since the call that made
   // them so.  On such rows every iteration of the reference's loop is a no-op on the state (babai finds |mu| <= eta,
@@ -353,14 +383,15 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
   {
     if (kappa_start > 0)
     {
-      const int bst = warp_babai<MAXQ>(v, s, kappa_start, kappa_start, sr_start, eta, lane, st.babai_iters);
+      const int bst =
+          warp_babai<MAXQ, COOP>(v, s, kappa_start, kappa_start, sr_start, eta, lane, st.babai_iters, nullptr, C);
       if (bst != RED_SUCCESS)
       {
         st.final_kappa = kappa_start, st.zeros = zeros;
         return bst;
       }
     }
-    if (!warp_update_gso_row(v, kappa_start, kappa_start, s, lane))
+    if (!lll_update_gso_row<COOP>(v, kappa_start, kappa_start, s, lane, C))
     {
       st.final_kappa = kappa_start, st.zeros = zeros;
       return RED_GSO_FAILURE;
@@ -388,7 +419,8 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     const long long tb_ = clock64();
     const long long cu_ = st.cyc_update;
 #endif
-    const int bst = warp_babai<MAXQ>(v, s, kappa, kappa, sr_start, eta, lane, st.babai_iters, &st.cyc_update);
+    const int bst =
+        warp_babai<MAXQ, COOP>(v, s, kappa, kappa, sr_start, eta, lane, st.babai_iters, &st, C);
 #ifdef B200_LLL_PROFILE
     st.cyc_babai += (clock64() - tb_) - (st.cyc_update - cu_);
     const long long tl_ = clock64();

@@ -22,9 +22,11 @@ def gso_profile(b):
     return np.array([s["r"][i, i] for i in range(b.shape[0])])
 
 
-def test_bkz20_without_pruning_walks_the_reference_trajectory(fb):
+@pytest.mark.parametrize("lll_kernel", ["cta", "warp"])
+def test_bkz20_without_pruning_walks_the_reference_trajectory(fb, lll_kernel, monkeypatch):
     """No pruning => no rerandomisation => BKZ is deterministic: device LLL (bit-identical to the reference's) +
     device enumeration (same best vector) must end on the SAME basis as the reference's bkz_reduction."""
+    monkeypatch.setenv("B200_LLL_CTA", "1" if lll_kernel == "cta" else "0")
     z = H.gold("bkz_q60.npz")
     b = z["b_in"].copy()
     st, stats = fb.bkz_reduction(b, fb.BKZParam(20, strategies=None, flags=fb.BKZ_NO_LLL))

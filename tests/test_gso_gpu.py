@@ -17,6 +17,14 @@ def fb():
     return fplll_b200
 
 
+@pytest.fixture(params=["cta", "warp"])
+def lll_mode(request, monkeypatch):
+    """Both device LLL kernels: one CTA per lattice with the Babai iteration shared between its warps (gso_cta.cuh,
+    taken for small batches) and one warp per lattice (taken for large batches); B200_LLL_CTA selects."""
+    monkeypatch.setenv("B200_LLL_CTA", "1" if request.param == "cta" else "0")
+    return request.param
+
+
 def _gold_state(z, prefix=""):
     g = lambda k: z[prefix + k]
     return dict(n_known_rows=int(g("n_known_rows")), n_known_cols=int(g("n_known_cols")),
@@ -125,7 +133,7 @@ def test_gso_failure_reported_like_reference(fb):
     assert not md.update_gso_row(2).any()
 
 
-def test_device_lll_u40_equals_reference_basis(fb):
+def test_device_lll_u40_equals_reference_basis(fb, lll_mode):
     """BASELINE config #1: LLL delta=0.99 on latticegen u 40 40 — the device LLL must walk the reference's exact
     basis trajectory (same swaps, same output basis as MatGSO<long,double>+LLLReduction of the reference)."""
     z = H.gold("u40_lll_long.npz")
@@ -137,7 +145,7 @@ def test_device_lll_u40_equals_reference_basis(fb):
 
 
 @pytest.mark.parametrize("seed,d,bits", [(21, 16, 20), (22, 48, 30), (23, 70, 16)])
-def test_device_lll_random_vs_oracle(fb, seed, d, bits):
+def test_device_lll_random_vs_oracle(fb, lll_mode, seed, d, bits):
     rng = np.random.default_rng(seed)
     B = 5
     b = rng.integers(-(1 << bits), 1 << bits, size=(B, d, d), dtype=np.int64)
@@ -156,7 +164,7 @@ def test_device_lll_random_vs_oracle(fb, seed, d, bits):
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not shipped")
-def test_device_lll_output_passes_reference_is_lll_reduced(fb, tmp_path):
+def test_device_lll_output_passes_reference_is_lll_reduced(fb, lll_mode, tmp_path):
     """the reference's own acceptance check: is_lll_reduced<Z_NR<mpz_t>, FP_NR<mpfr_t>> (lll.cpp:226-258)."""
     z = H.gold("u40_lll_long.npz")
     b = z["b_in"].copy()
@@ -168,7 +176,7 @@ def test_device_lll_output_passes_reference_is_lll_reduced(fb, tmp_path):
 
 
 @pytest.mark.parametrize("seed,d,bits", [(31, 140, 10), (32, 200, 8)])
-def test_device_lll_wide_vs_oracle(fb, seed, d, bits):
+def test_device_lll_wide_vs_oracle(fb, lll_mode, seed, d, bits):
     """d > 128 takes the 8-registers-per-lane Babai path (k_lll<8>) that BKZ on dim-200 uses."""
     rng = np.random.default_rng(seed)
     b = rng.integers(-(1 << bits), 1 << bits, size=(2, d, d + 1), dtype=np.int64)
@@ -183,7 +191,7 @@ def test_device_lll_wide_vs_oracle(fb, seed, d, bits):
         assert np.array_equal(out[l], mo.state()["b"]), "lattice %d basis" % l
 
 
-def test_ranged_lll_and_size_reduction_resume_are_exact(fb):
+def test_ranged_lll_and_size_reduction_resume_are_exact(fb, lll_mode):
     """lll(0,0,k) / size_reduction(0,k) resume after the clean prefix; the result must equal a from-scratch oracle run
     of the same call sequence (BKZ's pattern: reduce a prefix, touch a row, reduce a longer prefix)."""
     import ctypes as C
