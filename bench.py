@@ -359,6 +359,18 @@ def main():
                          "nodes_per_s": n / float(dt[0])}
         except Exception as ex:
             enum_dist = {"error": str(ex)[:300]}
+    # BKZ-60 wall-seconds at N GPUs: one driver (rank 0) with GSO/LLL on its GPU and every enumeration's subtree roots
+    # dealt over all N devices of the box (include/b200bkz.h: devices[]).  The other ranks wait on a CPU (gloo) barrier
+    # so that no NCCL kernel sits on the GPUs rank 0 launches its cooperative enumeration kernels on.
+    bkz_multi = None
+    if dist and not a.no_extras and not a.no_bkz:
+        try:
+            cpu_group = dist.new_group(backend="gloo")
+            if rank == 0:
+                bkz_multi = bkz_extras(local, devices=list(range(world)), with_ref=False)
+            dist.barrier(group=cpu_group)
+        except Exception as ex:
+            bkz_multi = {"error": str(ex)[:300]}
     if rank == 0:
         peak, peak_src = peaks()
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
@@ -377,10 +389,8 @@ def main():
                 "gpu_launches": 2 * a.steps, "clocks": clocks}
         if not a.no_extras and world > 1 and enum_dist is not None:
             line["enum"] = enum_dist
-            if not a.no_bkz:
-                # BKZ-60 wall-seconds at N GPUs: one driver (rank 0), GSO/LLL on its GPU, every enumeration's subtree
-                # roots dealt over all N devices of the box (include/b200bkz.h: devices[])
-                line["bkz60"] = bkz_extras(local, devices=list(range(world)), with_ref=False)
+            if bkz_multi is not None:
+                line["bkz60"] = bkz_multi
         if not a.no_extras and world == 1:
             line["enum"] = enum_extras(local)
             line["householder"] = hh_extras(local)
