@@ -364,13 +364,17 @@ def main():
     # so that no NCCL kernel sits on the GPUs rank 0 launches its cooperative enumeration kernels on.
     bkz_multi = None
     if dist and not a.no_extras and not a.no_bkz:
+        cpu_group = None
         try:
             cpu_group = dist.new_group(backend="gloo")
-            if rank == 0:
-                bkz_multi = bkz_extras(local, devices=list(range(world)), with_ref=False)
-            dist.barrier(group=cpu_group)
         except Exception as ex:
-            bkz_multi = {"error": str(ex)[:300]}
+            bkz_multi = {"error": "gloo group: " + str(ex)[:300]}
+        if cpu_group is not None:
+            try:
+                if rank == 0:
+                    bkz_multi = bkz_extras(local, devices=list(range(world)), with_ref=False)  # catches its own errors
+            finally:
+                dist.barrier(group=cpu_group)  # always reached: the other ranks are waiting in it
     if rank == 0:
         peak, peak_src = peaks()
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,

@@ -57,6 +57,60 @@ __device__ inline void coop_post(CoopShared *C, int cmd, int a0, int a1, int a2,
   cta_bar(1);
 }
 
+// The Gram dot product for a lone warp: same ordered chain as lane_dot (gso_warp.cuh), but 16 loads per group,
+// double-buffered (32 in flight) — with nobody to hide an L2 round trip behind, the 8-deep form spends 25 trips on a
+// 201-column row — and the tail fetched as one predicated group.
+__device__ inline double lane_dot_deep(const double *__restrict__ col, const double *vec, int ncols)
+{
+  constexpr int DEPTH = 16;
+  double acc   = __dmul_rn(col[0], vec[0]);
+  const int k0 = 1, ng = (ncols - k0) / DEPTH;
+  double x[DEPTH], y[DEPTH];
+  if (ng > 0)
+  {
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++)
+      x[u] = col[(size_t)(k0 + u) * 32];
+  }
+  for (int g = 0; g < ng; g += 2)
+  {
+    const int k = k0 + DEPTH * g;
+    if (g + 1 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++)
+        y[u] = col[(size_t)(k + DEPTH + u) * 32];
+    }
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++)
+      acc = __dadd_rn(acc, __dmul_rn(x[u], vec[k + u]));
+    if (g + 2 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++)
+        x[u] = col[(size_t)(k + 2 * DEPTH + u) * 32];
+    }
+    if (g + 1 < ng)
+    {
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++)
+        acc = __dadd_rn(acc, __dmul_rn(y[u], vec[k + DEPTH + u]));
+    }
+  }
+  const int kt = k0 + DEPTH * ng, rem = ncols - kt;
+  if (rem > 0)
+  {
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++)
+      x[u] = (u < rem) ? col[(size_t)(kt + u) * 32] : 0.0;
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++)
+      if (u < rem)
+        acc = __dadd_rn(acc, __dmul_rn(x[u], vec[kt + u]));
+  }
+  return acc;
+}
+
 // ---- UPDATE ---------------------------------------------------------------------------------------------------------
 // update_gso_row(i, last_j) for a row that is already discovered and has valid[i] <= last_j (the master checks both).
 // Same arithmetic as warp_update_gso_row: lane l of panel p owns column j = 32p + l,
@@ -102,7 +156,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
       double g = gfrow[j];
       if (g != g)
       {
-        g        = lane_dot(v.bf + bf_off(j, 0, n), s.vb, ncols);
+        g        = lane_dot_deep(v.bf + bf_off(j, 0, n), s.vb, ncols);
         gfrow[j] = g;
       }
       a = lane_chain<true>(g, v.mu + mu_panel_base(p) + lane, s.rrow, 0, 32 * p0);
@@ -195,15 +249,19 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
     cta_bar(2);
     for (int k = tid; k < i; k += CTA_WARPS * 32)
       s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
+    const bool gnan = (gfrow[i] != gfrow[i]);  // then s.vb holds bf_i: square it in place, the chain below only adds
+    if (gnan)
+      for (int c = tid; c < ncols; c += CTA_WARPS * 32)
+        s.vb[c] = __dmul_rn(s.vb[c], s.vb[c]);
     cta_bar(2);
     if (tid == 0)
     {
       double g = gfrow[i];
-      if (g != g)
+      if (gnan)
       {
-        g = __dmul_rn(s.vb[0], s.vb[0]);
+        g = s.vb[0];
         for (int c = 1; c < ncols; c++)
-          g = __dadd_rn(g, __dmul_rn(s.vb[c], s.vb[c]));
+          g = __dadd_rn(g, s.vb[c]);
         gfrow[i] = g;
       }
       double a = g;

@@ -300,13 +300,20 @@ __device__ inline double warp_get_gram_diag(const View &v, WarpSmem &s, int i, i
   if (val != val)
   {
     const int ncols = v.meta[M_NKC];
-    warp_stage_bf_row(v, i, ncols, s.vb, lane);
+    // stage bf_i squared (one correctly rounded product per element, in parallel): the ordered chain only adds
+    const int64_t *brow = v.b + (size_t)i * v.ldb;
+    const int e         = v.row_expo_en ? -v.row_expo[i] : 0;
+    for (int c = lane; c < ncols; c += 32)
+    {
+      const double f = ldexp((double)brow[c], e);
+      s.vb[c]        = __dmul_rn(f, f);
+    }
     __syncwarp();
     if (lane == 0)
     {
-      double a = __dmul_rn(s.vb[0], s.vb[0]);
+      double a = s.vb[0];
       for (int c = 1; c < ncols; c++)
-        a = __dadd_rn(a, __dmul_rn(s.vb[c], s.vb[c]));
+        a = __dadd_rn(a, s.vb[c]);
       *g = a;
     }
     __syncwarp();
