@@ -219,6 +219,12 @@ def bkz_extras(local, devices=None, with_ref=True):
     return out
 
 
+def bkz_child(ndev):
+    """`bench.py --bkz-child N`: the N-device BKZ-60 tour in a process of its own (one JSON line on stdout)."""
+    print(json.dumps(bkz_extras(0, devices=list(range(ndev)), with_ref=False)))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,7 +235,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the enumeration / Householder / BKZ figures")
     ap.add_argument("--no-bkz", action="store_true", help="skip the BKZ-60 tour (about 1.5 min GPU + 1-2 min CPU reference)")
+    ap.add_argument("--bkz-child", type=int, default=0, help=argparse.SUPPRESS)
     a = ap.parse_args()
+    if a.bkz_child:
+        return bkz_child(a.bkz_child)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -372,7 +381,17 @@ def main():
         if cpu_group is not None:
             try:
                 if rank == 0:
-                    bkz_multi = bkz_extras(local, devices=list(range(world)), with_ref=False)  # catches its own errors
+                    # in a child process: a failure of the multi-device path must not take the headline line with it
+                    try:
+                        env = {k: v for k, v in os.environ.items()
+                               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+                        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--bkz-child", str(world)],
+                                           capture_output=True, text=True, timeout=420, env=env)
+                        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+                        bkz_multi = json.loads(lines[-1]) if lines else {"error": "child rc %d: %s" % (
+                            p.returncode, p.stderr[-300:])}
+                    except Exception as ex:
+                        bkz_multi = {"error": str(ex)[:300]}
             finally:
                 dist.barrier(group=cpu_group)  # always reached: the other ranks are waiting in it
     if rank == 0:

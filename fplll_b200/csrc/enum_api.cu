@@ -29,6 +29,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <deque>
 
 namespace {
 
@@ -444,7 +445,7 @@ struct DevCtx
   unsigned long long *h_words = nullptr, *h_nodes = nullptr;
 };
 std::mutex g_mu;
-std::vector<DevCtx> g_ctx;
+std::deque<DevCtx> g_ctx;  // deque: get_ctx hands out pointers that must survive later push_backs
 
 int get_ctx(int device, DevCtx **out)
 {
