@@ -387,7 +387,12 @@ __host__ __device__ inline size_t cta_smem_doubles(int d, int n)
 template <int MAXQ>
 __global__ void __launch_bounds__(CTA_WARPS * 32)
     k_lll_cta(Batch S, int mode, double delta, double eta, int kmin, int kstart, int kend, int sr_start, int *status,
-              long *stats)
+              long *stats
+#if B200_MU_CACHE
+              ,
+              int mu_panels
+#endif
+    )
 {
   extern __shared__ __align__(16) double smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, l = blockIdx.x;
@@ -412,9 +417,21 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
     C->v = v;
     C->s = s;
     C->bm = bm;
+#if B200_MU_CACHE
+    C->mu_s = bm + (size_t)((S.d + 32 + 1) & ~1);
+    C->mu_s_panels = mu_panels;
+#endif
     C->cmd = COOP_EXIT, C->flag = 1;
   }
   __syncwarp();
+#if B200_MU_CACHE
+  if (mu_panels > 0)
+  {
+    // shared-memory cache of the leading mu panels: every row the call can touch is < kend
+    coop_post(C, COOP_MULOAD, 0, (kend - 1) >> 5, 0, lane);
+    cta_mu_load(*C, 0, (kend - 1) >> 5, 0, lane);
+  }
+#endif
   LLLStats st;
   st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
   int r;
@@ -706,7 +723,7 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   for (const void *f : fns)
     CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   {
-    const int sm = (int)(cta_smem_doubles(d, n) * sizeof(double));
+    const int sm = B200_MU_CACHE ? 227 * 1024 : (int)(cta_smem_doubles(d, n) * sizeof(double));
     CK(cudaFuncSetAttribute((const void *)k_lll_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CK(cudaFuncSetAttribute((const void *)k_lll_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CK(cudaFuncSetAttribute((const void *)k_lll_cta<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -1009,14 +1026,27 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
   const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
   if (cta_on && S.B <= cta_max && S.d > 32)
   {
-    const size_t sm = cta_smem_doubles(S.d, S.n) * sizeof(double);
+    size_t sm = cta_smem_doubles(S.d, S.n) * sizeof(double);
+#if B200_MU_CACHE
+#define LLL_CTA_EXTRA_ARG , mu_panels
+    int mu_panels = 0;
+    if (getenv("B200_LLL_MU_SMEM") && atoi(getenv("B200_LLL_MU_SMEM")))
+    {
+      // opt-in (not yet measured): cache as many leading mu panels as fit into the 227 KB of the CTA
+      while (mu_panels < n_panels(S.d) && sm + mu_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
+        mu_panels++;
+      sm += mu_panel_base(mu_panels) * sizeof(double);
+    }
+#else
+#define LLL_CTA_EXTRA_ARG
+#endif
     long *d_stats_c = (stats && mode == 0) ? h->d_stats : nullptr;
     if (S.d <= 128)
-      k_lll_cta<4><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+      k_lll_cta<4><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
     else if (S.d <= 256)
-      k_lll_cta<8><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+      k_lll_cta<8><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
     else
-      k_lll_cta<16><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c);
+      k_lll_cta<16><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
     CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
     if (stats)
     {

@@ -23,21 +23,58 @@
 #pragma once
 #include "gso_warp.cuh"
 
+// Compile-time switch for the shared-memory cache of the leading mu panels (see CoopShared::mu_s).  Written at the end
+// of round 1 without GPU time left to measure it, so it is compiled OUT by default: build with -DB200_MU_CACHE=1 and run
+// with B200_LLL_MU_SMEM=1 to try it.
+#ifndef B200_MU_CACHE
+#define B200_MU_CACHE 0
+#endif
+
 namespace b200 {
 
 constexpr int CTA_WARPS = 8;
 constexpr int CTA_OWN   = 2;  // panels a warp can own: 16 panels = d <= 512
 
-enum { COOP_EXIT = 0, COOP_UPDATE = 1, COOP_BACKSUB = 2, COOP_IGEMV = 3 };
+enum { COOP_EXIT = 0, COOP_UPDATE = 1, COOP_BACKSUB = 2, COOP_IGEMV = 3, COOP_MULOAD = 4 };
 
 struct CoopShared
 {
   View v;      // the master's view (its metadata pointers point into the master's shared-memory cache)
   WarpSmem s;  // the master's scratch rows (vb, rrow, murow, aux, xs)
   double *bm;  // babai_mu row handed to BACKSUB
+#if B200_MU_CACHE
+  // Optional shared-memory cache of the leading mu panels (B200_LLL_MU_SMEM=1; off by default until measured): global
+  // memory stays authoritative — every writer of mu in the LLL path writes through or refreshes the cached copy — and the
+  // readers of the cooperative operations take panels < mu_s_panels from here, so that the kappa-deep serial chains pay
+  // shared-memory instead of L2 latency per tile.
+  double *mu_s;
+  int mu_s_panels;
+#endif
   int cmd, a0, a1, a2;
   int flag;
 };
+
+#if B200_MU_CACHE
+__device__ inline const double *coop_mu_panel(const CoopShared &C, int p)
+{
+  return (p < C.mu_s_panels) ? C.mu_s + mu_panel_base(p) : C.v.mu + mu_panel_base(p);
+}
+__device__ inline void coop_mu_store(CoopShared &C, int i, int k, double val)
+{
+  C.v.mu[mu_off(i, k)] = val;
+  if ((i >> 5) < C.mu_s_panels)
+    C.mu_s[mu_off(i, k)] = val;
+}
+__device__ inline double coop_mu_load(const CoopShared &C, int i, int k)
+{
+  return coop_mu_panel(C, i >> 5)[(size_t)k * 32 + (i & 31)];
+}
+#else
+// cache compiled out: the plain global-memory expressions (`v` is the operation's `const View &v = C.v`)
+#define coop_mu_panel(C_, p_) (v.mu + mu_panel_base(p_))
+#define coop_mu_store(C_, i_, k_, val_) (v.mu[mu_off((i_), (k_))] = (val_))
+#define coop_mu_load(C_, i_, k_) (v.mu[mu_off((i_), (k_))])
+#endif
 
 __device__ inline void cta_bar(int id)
 {
@@ -159,7 +196,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
         g        = lane_dot_deep(v.bf + bf_off(j, 0, n), s.vb, ncols);
         gfrow[j] = g;
       }
-      a = lane_chain<true>(g, v.mu + mu_panel_base(p) + lane, s.rrow, 0, 32 * p0);
+      a = lane_chain<true>(g, coop_mu_panel(C, p) + lane, s.rrow, 0, 32 * p0);
     }
     else if (p <= pl && j < j0)
       a = s.rrow[j];  // already-valid r(i,j): only broadcast in the triangle below
@@ -180,7 +217,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
           const int j        = 32 * sp + lane;
           const bool a_      = act[u];
           double a           = acc[u];
-          const double *tile = v.mu + mu_panel_base(sp) + lane + (size_t)(32 * sp) * 32;
+          const double *tile = coop_mu_panel(C, sp) + lane + (size_t)(32 * sp) * 32;
           double rd          = 1.0;
           double m[8], mn[8];
 #pragma unroll
@@ -217,7 +254,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
             rrow_g[j]          = a;
             s.rrow[j]          = a;
             const double mm    = __ddiv_rn(a, rd);
-            v.mu[mu_off(i, j)] = mm;
+            coop_mu_store(C, i, j, mm);
             s.murow[j]         = mm;
             if (!isfinite(mm))
               ok = false;
@@ -232,7 +269,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
     {
       const int p = p0 + w + CTA_WARPS * u;
       if (p > sp && act[u])
-        acc[u] = lane_chain<true>(acc[u], v.mu + mu_panel_base(p) + lane, s.rrow, 32 * sp, 32 * sp + 32);
+        acc[u] = lane_chain<true>(acc[u], coop_mu_panel(C, p) + lane, s.rrow, 32 * sp, 32 * sp + 32);
     }
   }
   if (!ok)
@@ -245,7 +282,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
   {
     // diagonal r(i,i) = g(i,i) - sum_{k<i} mu(i,k) r(i,k): products in parallel, one ordered subtraction chain
     for (int k = tid; k < min(j0, i); k += CTA_WARPS * 32)
-      s.murow[k] = v.mu[mu_off(i, k)];
+      s.murow[k] = coop_mu_load(C, i, k);
     cta_bar(2);
     for (int k = tid; k < i; k += CTA_WARPS * 32)
       s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
@@ -268,7 +305,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
       for (int k = 0; k < i; k++)
         a = __dsub_rn(a, s.aux[k]);
       rrow_g[i]          = a;
-      v.mu[mu_off(i, i)] = a;  // diagonal mirror
+      coop_mu_store(C, i, i, a);  // diagonal mirror
     }
   }
   if (tid == 0)
@@ -307,7 +344,7 @@ __device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_
         {
           double a              = val[u];
           const int kcol        = 32 * p + lane;
-          const double *tilecol = v.mu + mu_panel_base(p) + (size_t)kcol * 32;  // mu(32p+t, kcol) at [t]
+          const double *tilecol = coop_mu_panel(C, p) + (size_t)kcol * 32;  // mu(32p+t, kcol) at [t]
           unsigned nzmask       = 0;
           double tc[32];
 #pragma unroll
@@ -346,7 +383,7 @@ __device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_
         const int k = 32 * q + lane;
         if (q < p && q >= p_lo && k >= sr_start)
         {
-          const double *col = v.mu + mu_panel_base(p) + (size_t)k * 32;
+          const double *col = coop_mu_panel(C, p) + (size_t)k * 32;
           double a          = val[u];
           double cv[32];  // mu(32p + t, k), t = 0..31: 32 independent loads in flight
 #pragma unroll
@@ -409,6 +446,38 @@ __device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int l
   cta_bar(2);
 }
 
+#if B200_MU_CACHE
+// ---- MULOAD --------------------------------------------------------------------------------------------------------
+// (re)fill the shared-memory copies of the mu panels pa..pb (those that are cached) from global memory
+__device__ inline void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
+{
+  const int tid = threadIdx.x;
+  const int hi  = min(pb, C.mu_s_panels - 1);
+  for (int p = max(pa, 0); p <= hi; ++p)
+  {
+    const size_t base = mu_panel_base(p);
+    const int cnt     = 32 * 32 * (p + 1);
+    const double *src = C.v.mu + base;
+    double *dst       = C.mu_s + base;
+    int t = tid;
+    for (; t + 7 * CTA_WARPS * 32 < cnt; t += 8 * CTA_WARPS * 32)
+    {
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        x[u] = src[t + u * CTA_WARPS * 32];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        dst[t + u * CTA_WARPS * 32] = x[u];
+    }
+    for (; t < cnt; t += CTA_WARPS * 32)
+      dst[t] = src[t];
+  }
+  cta_bar(2);
+}
+
+#endif
+
 // helper warps: wait for commands until the master says EXIT
 __device__ inline void coop_helper_loop(CoopShared &C, int w, int lane)
 {
@@ -424,6 +493,10 @@ __device__ inline void coop_helper_loop(CoopShared &C, int w, int lane)
       cta_backsub(C, a0, a1, a2, w, lane);
     else if (cmd == COOP_IGEMV)
       cta_igemv(C, a0, a1, w, lane);
+#if B200_MU_CACHE
+    else if (cmd == COOP_MULOAD)
+      cta_mu_load(C, a0, a1, w, lane);
+#endif
   }
 }
 
@@ -439,9 +512,44 @@ __device__ inline bool lll_update_gso_row(const View &v, int i, int last_j, Warp
   if (j0 > last_j)
     return true;
   if (i < 32)
-    return warp_update_gso_row(v, i, last_j, s, lane);  // a single panel: nothing to share
+  {
+    // a single panel: nothing to share.  The one-warp routine writes mu(i, .) to global memory only: refresh the
+    // cached copy of that row (mu_off(i, k) = 32 k + i in panel 0)
+    const bool ok = warp_update_gso_row(v, i, last_j, s, lane);
+#if B200_MU_CACHE
+    if (C->mu_s_panels > 0)
+    {
+      __syncwarp();
+      C->mu_s[32 * lane + i] = v.mu[32 * lane + i];
+      __syncwarp();
+    }
+#endif
+    return ok;
+  }
   coop_post(C, COOP_UPDATE, i, last_j, 0, lane);
   return cta_update_gso_row(*C, i, last_j, 0, lane);
 }
+
+// master: after a one-warp routine rewrote parts of mu in global memory (move_row: rows lo..hi rotate; set_r: the
+// diagonal mirror), bring the cached panels back in line
+#if B200_MU_CACHE
+template <bool COOP> __device__ inline void lll_mu_reload(CoopShared *C, int row_lo, int row_hi, int lane)
+{
+  if (!COOP || C->mu_s_panels == 0 || (row_lo >> 5) >= C->mu_s_panels)
+    return;
+  coop_post(C, COOP_MULOAD, row_lo >> 5, row_hi >> 5, 0, lane);
+  cta_mu_load(*C, row_lo >> 5, row_hi >> 5, 0, lane);
+}
+template <bool COOP> __device__ inline void lll_mu_refresh_diag(CoopShared *C, int i, int lane)
+{
+  if (!COOP || (i >> 5) >= C->mu_s_panels)
+    return;
+  __syncwarp();
+  if (lane == 0)
+    C->mu_s[mu_off(i, i)] = C->v.mu[mu_off(i, i)];
+  __syncwarp();
+}
+
+#endif
 
 }  // namespace b200

@@ -10,6 +10,17 @@
 
 namespace b200 {
 
+// mu(i,k) as the LLL code reads it: through the CTA's shared-memory cache when that is compiled in (gso_cta.cuh)
+#if B200_MU_CACHE
+#define LLL_MU_LOAD(i_, k_) (COOP ? coop_mu_load(*C, (i_), (k_)) : v.mu[mu_off((i_), (k_))])
+#define LLL_MU_RELOAD(lo_, hi_) lll_mu_reload<COOP>(C, (lo_), (hi_), lane)
+#define LLL_MU_REFRESH_DIAG(i_) lll_mu_refresh_diag<COOP>(C, (i_), lane)
+#else
+#define LLL_MU_LOAD(i_, k_) (v.mu[mu_off((i_), (k_))])
+#define LLL_MU_RELOAD(lo_, hi_) ((void)0)
+#define LLL_MU_REFRESH_DIAG(i_) ((void)0)
+#endif
+
 enum { RED_SUCCESS = 0, RED_GSO_FAILURE = 2, RED_BABAI_FAILURE = 3, RED_LLL_FAILURE = 4 };  // defs.h:153-169
 constexpr long SIZE_RED_FAILURE_THRESH = 5;                                                    // defs.h:146
 
@@ -62,7 +73,7 @@ __device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_e
       bm[q]       = 0.0;
       if (k < sr_end)
       {
-        bm[q]          = v.mu[mu_off(kappa, k)];
+        bm[q]          = LLL_MU_LOAD(kappa, k);
         const long de  = v.row_expo_en ? (long)(ek - v.row_expo[k]) : 0;
         s.xs[k]        = 0.0;
         if (k >= sr_start)
@@ -385,7 +396,10 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     kappa = max(kappa, min(v.meta[M_CLEAN_LLL], kappa_end));
   __syncwarp();
   for (; zeros < d && warp_b_row_is_zero(v, 0, lane); zeros++)
+  {
     warp_move_row(v, kappa_min, kappa_end - 1 - zeros, lane);
+    LLL_MU_RELOAD(kappa_min, kappa_end - 1 - zeros);
+  }
   if (zeros < d)
   {
     if (kappa_start > 0)
@@ -440,7 +454,7 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     // Lovasz test (lll.cpp:110-122): prefix chain lov[i] = lov[i-1] - mu(kappa,i-1) * r(kappa,i-1)
     const double g = warp_get_gram_diag(v, s, kappa, lane);
     for (int k = lane; k < kappa; k += 32)
-      s.aux[k] = __dmul_rn(v.mu[mu_off(kappa, k)], v.r[tri_off(kappa) + k]);
+      s.aux[k] = __dmul_rn(LLL_MU_LOAD(kappa, k), v.r[tri_off(kappa) + k]);
     __syncwarp();
     int new_kappa = kappa, action = 0;  // 0: accept, 1: move_row(old_k,new_kappa), 2: zero vector
     if (lane == 0)
@@ -479,18 +493,21 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
       if (action == 1)
       {
         warp_move_row(v, old_k, new_kappa, lane);
+        LLL_MU_RELOAD(new_kappa, old_k);
         kappa = new_kappa;
       }
       else
       {
         zeros++;
         warp_move_row(v, old_k, kappa_end - zeros, lane);
+        LLL_MU_RELOAD(old_k, kappa_end - zeros);
         kappa = old_k;
         continue;
       }
     }
     __syncwarp();
     warp_set_r(v, kappa, kappa, lov[kappa], lane);
+    LLL_MU_REFRESH_DIAG(kappa);
     kappa++;
 #ifdef B200_LLL_PROFILE
     st.cyc_move += clock64() - tm_;
