@@ -11,9 +11,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--fmad=false", "-Xcompiler", "-fPIC", "-shared"]
 
 TARGETS = {
-    "libb200gso.so": ["gso_api.cu"],
+    "libb200gso.so": ["gso_api.cu", "gso_lll_api.cu", "gso_lll_cta_api.cu"],
     "libb200enum.so": ["enum_api.cu"],
-    "libb200bkz.so": ["gso_api.cu", "enum_api.cu", "bkz_api.cu"],
+    "libb200bkz.so": ["gso_api.cu", "gso_lll_api.cu", "gso_lll_cta_api.cu", "enum_api.cu", "bkz_api.cu"],
     "libb200hh.so": ["hh_api.cu"],
 }
 
@@ -27,8 +27,9 @@ def _stale(out, srcs):
 
 
 def build_all(force=False, verbose=False):
-    """Each .cu is compiled ONCE to an object (the four translation units in parallel; gso_api.cu alone takes minutes:
-    three Babai widths x two LLL kernels, fully unrolled), then every library is linked from the objects it needs."""
+    """Each .cu is compiled ONCE to an object, all translation units in parallel (the LLL kernels — three Babai widths,
+    fully unrolled — live in units of their own because they take minutes), then every library is linked from the objects
+    it needs.  No --split-compile: its code generation is not reproducible from run to run."""
     from concurrent.futures import ThreadPoolExecutor
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
@@ -39,7 +40,7 @@ def build_all(force=False, verbose=False):
     def compile_unit(u):
         src, obj = os.path.join(CSRC, u), os.path.join(objdir, u[:-3] + ".o")
         if force or _stale(obj, [src]):
-            subprocess.check_call(["nvcc", "--split-compile", "0"] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+            subprocess.check_call(["nvcc"] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
         return obj
 
     with ThreadPoolExecutor(max_workers=len(units)) as ex:

@@ -4,91 +4,12 @@
 // With the panel-packed layout (gso_layout.cuh) every hot global access is a 256-byte coalesced warp load, so the
 // kernels are HBM-streaming: occupancy (16+ resident warps per SM, 8 independent loads in flight per lane in the
 // sweep loops) is what hides DRAM latency, not shared-memory tiling.  There is no CPU fallback anywhere.
-#include "../../include/b200gso.h"
-#include "gso_lll.cuh"
+#include "gso_common.cuh"
 #include "gso_tma.cuh"
-#include <cstdio>
-#include <algorithm>
-#include <cstring>
-#include <string>
-#include <vector>
 
-using namespace b200;
+thread_local std::string b200gso_g_err;
 
 namespace {
-
-constexpr int WARPS_PER_CTA = 4;
-thread_local std::string g_err;
-
-#define CK(call)                                                                                   \
-  do                                                                                               \
-  {                                                                                                \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess)                                                                         \
-    {                                                                                              \
-      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
-      return B200GSO_ECUDA;                                                                        \
-    }                                                                                              \
-  } while (0)
-
-// The LLL-family kernels (k_lll, k_size_reduction, k_apply_ops) are chains of short dependent steps on ONE lattice per
-// warp; every read of gso_valid_cols / row_expo / init_row_size / n_known_* from global memory is a ~0.5 us round trip
-// on the critical path.  MetaCache stages those arrays in shared memory for the lifetime of the kernel (the View's
-// pointers are simply re-pointed, every device routine keeps working unchanged) and writes them back at the end.
-struct MetaCache
-{
-  int *g_valid, *g_expo, *g_irs, *g_meta;
-  int d;
-  __host__ __device__ static size_t ints(int d) { return 3 * (size_t)((d + 3) & ~3) + M_STRIDE; }
-  __device__ void load(View &v, int *sm, int lane)
-  {
-    d = v.d;
-    const int dp = (d + 3) & ~3;
-    g_valid = v.valid, g_expo = v.row_expo, g_irs = v.irs, g_meta = v.meta;
-    int *s_valid = sm, *s_expo = sm + dp, *s_irs = sm + 2 * dp, *s_meta = sm + 3 * dp;
-    for (int i = lane; i < d; i += 32)
-    {
-      s_valid[i] = g_valid[i];
-      s_expo[i]  = g_expo[i];
-      s_irs[i]   = g_irs[i];
-    }
-    if (lane < M_STRIDE)
-      s_meta[lane] = g_meta[lane];
-    v.valid = s_valid, v.row_expo = s_expo, v.irs = s_irs, v.meta = s_meta;
-    __syncwarp();
-  }
-  __device__ void store(const View &v, int lane)
-  {
-    __syncwarp();
-    for (int i = lane; i < d; i += 32)
-    {
-      g_valid[i] = v.valid[i];
-      g_expo[i]  = v.row_expo[i];
-      g_irs[i]   = v.irs[i];
-    }
-    if (lane < M_STRIDE)
-      g_meta[lane] = v.meta[lane];
-  }
-};
-
-template <bool FULL_SMEM = true>
-__device__ inline bool warp_setup(const Batch &S, View &v, WarpSmem &s, double *&lov, int &lane)
-{
-  extern __shared__ __align__(16) double smem[];
-  const int w = threadIdx.x >> 5;
-  lane        = threadIdx.x & 31;
-  const int l = blockIdx.x * (blockDim.x >> 5) + w;
-  const size_t base = WarpSmem::doubles(S.d, S.n, FULL_SMEM);
-  const size_t per  = base + (FULL_SMEM ? (size_t)((S.d + 2 + 1) & ~1) + ((MetaCache::ints(S.d) + 1) >> 1) : 0);
-  s.carve(smem + (size_t)w * per, S.d, S.n, FULL_SMEM);
-  lov = FULL_SMEM ? smem + (size_t)w * per + base : nullptr;
-  if (l >= S.B)
-    return false;
-  v = S.view(l);
-  return true;
-}
-
-__device__ inline int *meta_scratch(const Batch &S, double *lov) { return (int *)(lov + ((S.d + 2 + 1) & ~1)); }
 
 // size_increased(), gso.cpp:368-403: init_row_size, zero-filled bf, update_bf for every row; fresh metadata.
 __global__ void k_init(Batch S)
@@ -343,143 +264,6 @@ __global__ void k_get_row(Batch S, int i, double *mu_row, double *r_row, int *va
     valid[l] = v.valid[i];
 }
 
-template <int MAXQ>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-    k_lll(Batch S, double delta, double eta, int kmin, int kstart, int kend, int sr_start, int *status, long *stats)
-{
-  View v;
-  WarpSmem s;
-  double *lov;
-  int lane;
-  if (!warp_setup(S, v, s, lov, lane))
-    return;
-  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  LLLStats st;
-  MetaCache mc;
-  mc.load(v, meta_scratch(S, lov), lane);
-  const int r = warp_lll<MAXQ>(v, s, lov, delta, eta, kmin, kstart, kend, sr_start, lane, st);
-  mc.store(v, lane);
-  if (lane == 0)
-  {
-    status[l] = r;
-    if (stats)
-    {
-      stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
-      stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
-#ifdef B200_LLL_PROFILE
-      // profiling builds (batch 1 only): overwrite final_kappa/zeros/babai_iters slots?  no — append after the batch block
-      long *px = stats + 4 * S.B;
-      px[0] = st.cyc_update, px[1] = st.cyc_babai, px[2] = st.cyc_lovasz, px[3] = st.cyc_move;
-#endif
-    }
-  }
-}
-
-// Single-lattice regime (BKZ): one CTA of CTA_WARPS warps per lattice, warp 0 runs the LLL / size-reduction control
-// flow and shares the O(kappa d) pieces of every Babai iteration with the other warps (gso_cta.cuh).
-// mode 0: lll(kmin, kstart, kend, sr_start); mode 1: size_reduction(kmin, kend, sr_start).
-__host__ __device__ inline size_t cta_smem_doubles(int d, int n)
-{
-  const size_t per = WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1) + ((((MetaCache::ints(d) + 1) >> 1) + 1) & ~(size_t)1);
-  return per + ((sizeof(CoopShared) + 15) / 16) * 2 + (size_t)((d + 32 + 1) & ~1);
-}
-
-template <int MAXQ>
-__global__ void __launch_bounds__(CTA_WARPS * 32)
-    k_lll_cta(Batch S, int mode, double delta, double eta, int kmin, int kstart, int kend, int sr_start, int *status,
-              long *stats
-#if B200_MU_CACHE
-              ,
-              int mu_panels
-#endif
-    )
-{
-  extern __shared__ __align__(16) double smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, l = blockIdx.x;
-  const size_t base = WarpSmem::doubles(S.d, S.n);
-  const size_t lovn = (size_t)((S.d + 2 + 1) & ~1);
-  const size_t per  = base + lovn + ((((MetaCache::ints(S.d) + 1) >> 1) + 1) & ~(size_t)1);
-  CoopShared *C     = reinterpret_cast<CoopShared *>(smem + per);
-  double *bm        = smem + per + ((sizeof(CoopShared) + 15) / 16) * 2;
-  if (w != 0)
-  {
-    coop_helper_loop(*C, w, lane);
-    return;
-  }
-  View v = S.view(l);
-  WarpSmem s;
-  s.carve(smem, S.d, S.n, true);
-  double *lov = smem + base;
-  MetaCache mc;
-  mc.load(v, (int *)(lov + lovn), lane);
-  if (lane == 0)
-  {
-    C->v = v;
-    C->s = s;
-    C->bm = bm;
-#if B200_MU_CACHE
-    C->mu_s = bm + (size_t)((S.d + 32 + 1) & ~1);
-    C->mu_s_panels = mu_panels;
-#endif
-    C->cmd = COOP_EXIT, C->flag = 1;
-  }
-  __syncwarp();
-#if B200_MU_CACHE
-  if (mu_panels > 0)
-  {
-    // shared-memory cache of the leading mu panels: every row the call can touch is < kend
-    coop_post(C, COOP_MULOAD, 0, (kend - 1) >> 5, 0, lane);
-    cta_mu_load(*C, 0, (kend - 1) >> 5, 0, lane);
-  }
-#endif
-  LLLStats st;
-  st.n_swaps = st.final_kappa = st.zeros = st.babai_iters = 0;
-  int r;
-  if (mode == 0)
-    r = warp_lll<MAXQ, true>(v, s, lov, delta, eta, kmin, kstart, kend, sr_start, lane, st, C);
-  else
-    r = warp_size_reduction<MAXQ, true>(v, s, kmin, kend, sr_start, eta, lane, st.babai_iters, C);
-  coop_post(C, COOP_EXIT, 0, 0, 0, lane);
-  mc.store(v, lane);
-  if (lane == 0)
-  {
-    status[l] = r;
-    if (stats)
-    {
-      stats[4 * l + 0] = st.n_swaps, stats[4 * l + 1] = st.final_kappa;
-      stats[4 * l + 2] = st.zeros, stats[4 * l + 3] = st.babai_iters;
-#ifdef B200_LLL_PROFILE
-      if (mode == 0)
-      {
-        long *px = stats + 4 * S.B;
-        px[0] = st.cyc_update, px[1] = st.cyc_babai, px[2] = st.cyc_lovasz, px[3] = st.cyc_move;
-        px[4] = st.cyc_gather, px[5] = st.cyc_backsub, px[6] = st.cyc_igemv, px[7] = st.cyc_ropend;
-      }
-#endif
-    }
-  }
-}
-
-template <int MAXQ>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-    k_size_reduction(Batch S, double eta, int kmin, int kend, int sr_start, int *status)
-{
-  View v;
-  WarpSmem s;
-  double *lov;
-  int lane;
-  if (!warp_setup(S, v, s, lov, lane))
-    return;
-  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  long iters  = 0;
-  MetaCache mc;
-  mc.load(v, meta_scratch(S, lov), lane);
-  const int r = warp_size_reduction<MAXQ>(v, s, kmin, kend, sr_start, eta, lane, iters);
-  mc.store(v, lane);
-  if (lane == 0)
-    status[l] = r;
-}
-
 __global__ void k_apply_ops(Batch S, const b200gso_op *ops, int n)
 {
   View v;
@@ -561,24 +345,6 @@ __global__ void k_get_block(Batch S, int l, int first, int beta, double *mut, do
 
 }  // namespace
 
-struct b200gso
-{
-  Batch S;
-  int device;
-  cudaStream_t stream;
-  size_t smem_bytes, smem_compact;
-  int *d_ok;      // batch ints
-  double *d_tmp;  // batch doubles
-  long *d_ltmp;   // batch longs
-  int64_t *d_rows;    // batch*n   (upload_row staging)
-  double *d_rowbuf;   // 2*batch*d (get_mu_r_row staging)
-  int *d_valid_i;     // batch
-  long *d_stats;      // 4*batch (LLL statistics)
-  double *d_blk;      // d*d + 2*d doubles + d longs (get_block / get_r_diag staging)
-  b200gso_op *d_ops;  // op-list staging (grown on demand)
-  size_t ops_cap;
-  std::vector<void *> allocs;
-};
 
 static int upd_variant()
 {
@@ -590,9 +356,7 @@ static int upd_variant()
   }
   return v;
 }
-static int grid_warps(const b200gso *h);
 static void launch_update_row(b200gso *h, int i, int last_j);
-static int grid_warps(const b200gso *h) { return (h->S.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
 
 static void launch_update_row(b200gso *h, int i, int last_j)
 {
@@ -717,17 +481,11 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row<8>, (const void *)k_update_row<6>, (const void *)k_update_row<5>,
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
-                       (const void *)k_lll<4>,       (const void *)k_lll<8>,       (const void *)k_lll<16>,
-                       (const void *)k_size_reduction<4>, (const void *)k_size_reduction<8>,
-                       (const void *)k_size_reduction<16>, (const void *)k_apply_ops};
+                       (const void *)k_apply_ops};
   for (const void *f : fns)
     CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  {
-    const int sm = B200_MU_CACHE ? 227 * 1024 : (int)(cta_smem_doubles(d, n) * sizeof(double));
-    CK(cudaFuncSetAttribute((const void *)k_lll_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute((const void *)k_lll_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute((const void *)k_lll_cta<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  }
+  if (b200gso_lll_warp_attrs(h->smem_bytes) || b200gso_lll_cta_attrs(d, n))
+    return B200GSO_ECUDA;
   CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
   CK(cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream));
   CK(cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream));
@@ -1026,27 +784,8 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
   const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
   if (cta_on && S.B <= cta_max && S.d > 32)
   {
-    size_t sm = cta_smem_doubles(S.d, S.n) * sizeof(double);
-#if B200_MU_CACHE
-#define LLL_CTA_EXTRA_ARG , mu_panels
-    int mu_panels = 0;
-    if (getenv("B200_LLL_MU_SMEM") && atoi(getenv("B200_LLL_MU_SMEM")))
-    {
-      // opt-in (not yet measured): cache as many leading mu panels as fit into the 227 KB of the CTA
-      while (mu_panels < n_panels(S.d) && sm + mu_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
-        mu_panels++;
-      sm += mu_panel_base(mu_panels) * sizeof(double);
-    }
-#else
-#define LLL_CTA_EXTRA_ARG
-#endif
-    long *d_stats_c = (stats && mode == 0) ? h->d_stats : nullptr;
-    if (S.d <= 128)
-      k_lll_cta<4><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
-    else if (S.d <= 256)
-      k_lll_cta<8><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
-    else
-      k_lll_cta<16><<<S.B, CTA_WARPS * 32, sm, h->stream>>>(S, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats_c LLL_CTA_EXTRA_ARG);
+    if (b200gso_lll_cta_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, (stats && mode == 0) ? h->d_stats : nullptr))
+      return B200GSO_ECUDA;
     CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
     if (stats)
     {
@@ -1060,22 +799,8 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
     CK(cudaGetLastError());
     return 0;
   }
-  const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
-#define LLL_LAUNCH(Q)                                                                                          \
-  do                                                                                                           \
-  {                                                                                                            \
-    if (mode == 0)                                                                                             \
-      k_lll<Q><<<g, t, h->smem_bytes, h->stream>>>(S, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats); \
-    else                                                                                                       \
-      k_size_reduction<Q><<<g, t, h->smem_bytes, h->stream>>>(S, eta, kmin, kend, sr_start, d_st);             \
-  } while (0)
-  if (S.d <= 128)
-    LLL_LAUNCH(4);
-  else if (S.d <= 256)
-    LLL_LAUNCH(8);
-  else
-    LLL_LAUNCH(16);
-#undef LLL_LAUNCH
+  if (b200gso_lll_warp_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats))
+    return B200GSO_ECUDA;
   CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
   if (stats)
   {
