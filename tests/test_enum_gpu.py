@@ -106,3 +106,19 @@ def test_reference_bkz_with_the_plugin_installed(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     assert "status=0" in p.stdout
     assert np.array_equal(np.array(O.read_matrix(out), dtype=np.int64), z["bkz20_none_b"])
+
+
+def test_two_devices_in_one_process_visit_the_same_nodes(en):
+    """b200enum_run(devices = [0, 1]): subtree roots dealt over two GPUs of the box from ONE process (what the BKZ driver
+    does with `devices`); fixed radius, so the per-level node counts must equal the oracle's.  Needs two GPUs."""
+    import ctypes
+    from fplll_b200._lib import load
+    if load("libb200enum.so").b200enum_device_count() < 2:
+        pytest.skip("one GPU visible")
+    z = H.gold("enum_r200_b30_unpruned.npz")
+    R = 0.55 * float(z["maxdist"])
+    ref = O.enum_svp(z["mut"], z["rdiag"], None, R, shrink=False)
+    for _ in range(2):  # second call: both device contexts already exist
+        res = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True, devices=[0, 1])
+        assert res["stats"]["n_devices"] == 2
+        assert np.array_equal(res["nodes"], ref["nodes"])
