@@ -111,8 +111,10 @@ def test_reference_bkz_with_the_plugin_installed(tmp_path):
 def test_two_devices_in_one_process_visit_the_same_nodes(en):
     """b200enum_run(devices = [0, 1]): subtree roots dealt over two GPUs of the box from ONE process (what the BKZ driver
     does with `devices`); fixed radius, so the per-level node counts must equal the oracle's.  Needs two GPUs."""
-    import ctypes
+    import os
     from fplll_b200._lib import load
+    if not os.environ.get("B200_TEST_MULTI_GPU"):
+        pytest.skip("set B200_TEST_MULTI_GPU=1 on a box with two GPUs (gpurun --gpus 2)")
     if load("libb200enum.so").b200enum_device_count() < 2:
         pytest.skip("one GPU visible")
     z = H.gold("enum_r200_b30_unpruned.npz")
