@@ -5,6 +5,7 @@
 // kernels are HBM-streaming: occupancy (16+ resident warps per SM, 8 independent loads in flight per lane in the
 // sweep loops) is what hides DRAM latency, not shared-memory tiling.  There is no CPU fallback anywhere.
 #include "gso_common.cuh"
+#include "gso_gram.cuh"
 #include "gso_tma.cuh"
 
 thread_local std::string b200gso_g_err;
@@ -138,6 +139,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_update_gso(Batch S, int 
     r = warp_update_gso_row(v, i, i, s, lane);
   if (ok && lane == 0)
     ok[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = r ? 1 : 0;
+}
+
+// Whole Gram matrix in 32 x 32 tiles (gso_gram.cuh): warp w of CTA (x, l) takes tile pair 4 x + w of lattice l.
+__global__ void __launch_bounds__(128) k_gram_tiles(Batch S, int mode)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  View v      = S.view(blockIdx.y);
+  const int P = n_panels(v.d), t = blockIdx.x * 4 + w;
+  if (t >= P * (P + 1) / 2)
+    return;
+  int pi, pj;
+  gram_pair(t, pi, pj);
+  const int ncols = v.meta[M_NKC];
+  if (mode == GRAM_DMMA)
+    warp_gram_tile_dmma(v, pi, pj, ncols, lane);
+  else
+    warp_gram_tile_ordered(v, pi, pj, ncols, lane);
 }
 
 __global__ void k_row_addmul_we(Batch S, int i, int j, const double *x, const long *expo_add)
@@ -612,6 +630,18 @@ int b200gso_update_gso(b200gso_t *h, int *ok)
   if (!h)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
+  k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_compact, h->stream>>>(h->S, h->d_ok);
+  return fetch_ok(h, ok);
+}
+
+int b200gso_update_gso_blocked(b200gso_t *h, int gram_mode, int *ok)
+{
+  if (!h || (gram_mode != B200GSO_GRAM_ORDERED && gram_mode != B200GSO_GRAM_DMMA) || h->S.B > 65535)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+  const int P = n_panels(h->S.d), pairs = P * (P + 1) / 2;
+  k_gram_tiles<<<dim3((pairs + 3) / 4, h->S.B), 128, 0, h->stream>>>(h->S, gram_mode);
   k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_compact, h->stream>>>(h->S, h->d_ok);
   return fetch_ok(h, ok);
 }

@@ -32,6 +32,7 @@ def _lib():
         L.b200gso_discover_all_rows.argtypes = [vp]
         L.b200gso_update_gso_row.argtypes = [vp, i, i, ip]
         L.b200gso_update_gso.argtypes = [vp, ip]
+        L.b200gso_update_gso_blocked.argtypes = [vp, i, ip]
         L.b200gso_row_addmul_we.argtypes = [vp, i, i, dp, lp]
         L.b200gso_row_op_begin.argtypes = [vp, i, i]
         L.b200gso_row_op_end.argtypes = [vp, i, i]
@@ -102,6 +103,13 @@ class MatGSO:
     def update_gso(self):
         ok = np.zeros(self.batch, np.int32)
         _ck(_lib().b200gso_update_gso(self._h, _ptr(ok, C.c_int)), "update_gso")
+        return ok.astype(bool)
+
+    def update_gso_blocked(self, gram_mode=0):
+        """EXPERIMENTAL: update_gso() with the Gram matrix recomputed in 32x32 tiles first (0: reference-order dot
+        products, 1: fp64 tensor-core DMMA) — include/b200gso.h."""
+        ok = np.zeros(self.batch, np.int32)
+        _ck(_lib().b200gso_update_gso_blocked(self._h, gram_mode, _ptr(ok, C.c_int)), "update_gso_blocked")
         return ok.astype(bool)
 
     def row_addmul_we(self, i, j, x, expo_add=0):

@@ -237,3 +237,46 @@ def test_ranged_lll_and_size_reduction_resume_are_exact(fb, lll_mode):
     assert dev_lll(60) == 0
     s3, bb = ora_lll(60)
     assert np.array_equal(md.b[0], bb)
+
+
+_experimental = pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_EXPERIMENTAL"),
+                                   reason="experimental entry points (not yet run on hardware): set B200_TEST_EXPERIMENTAL=1")
+
+
+@_experimental
+@pytest.mark.parametrize("mode", [0, 1])
+def test_blocked_update_gso_small_entries_bit_exact(fb, mode):
+    """b200gso_update_gso_blocked: Gram matrix in 32x32 tiles, then the row sweeps.  Entries below 2^20 make every
+    partial sum of a Gram entry exact, so the tensor-core (DMMA) mode must agree bit for bit as well."""
+    rng = np.random.default_rng(51)
+    b = rng.integers(-(1 << 20), 1 << 20, size=(3, 70, 75), dtype=np.int64)
+    b[1, :, 60:] = 0  # ragged: fewer known columns
+    md = fb.MatGSO(b)
+    assert md.update_gso_blocked(mode).all()
+    st = md.state()
+    for l in range(3):
+        mo = O.OracleGSO(b[l])
+        assert mo.update_gso()
+        H.assert_state_equal(H.lattice_state(st, l), mo.state(), "blocked mode %d lattice %d" % (mode, l))
+
+
+@_experimental
+def test_blocked_update_gso_large_entries(fb):
+    """40-bit entries: the ordered mode stays bit-exact, the DMMA mode is within north_star's 1e-9 on mu and r."""
+    rng = np.random.default_rng(52)
+    b = rng.integers(-(1 << 40), 1 << 40, size=(2, 64, 64), dtype=np.int64)
+    for mode in (0, 1):
+        md = fb.MatGSO(b)
+        assert md.update_gso_blocked(mode).all()
+        st = md.state()
+        for l in range(2):
+            mo = O.OracleGSO(b[l])
+            assert mo.update_gso()
+            s = mo.state()
+            if mode == 0:
+                H.assert_state_equal(H.lattice_state(st, l), s, "ordered lattice %d" % l)
+            else:
+                for i in range(64):
+                    for name in ("mu", "r"):
+                        a, e = st[name][l][i, :i], s[name][i, :i]
+                        assert np.all(np.abs(a - e) <= 1e-9 * np.maximum(1.0, np.abs(e))), (name, l, i)

@@ -69,6 +69,16 @@ def main():
         out["M2"].append(rec)
         print("M2", json.dumps(rec), flush=True)
         m.close()
+        if os.environ.get("B200_TEST_EXPERIMENTAL"):  # blocked Gram (gso_gram.cuh): 0 = ordered, 1 = DMMA
+            for mode in (0, 1):
+                m = MatGSO(rand_basis(rng, B, d, n), GSO_ROW_EXPO)
+                m.sync()
+                t = time.perf_counter()
+                ok = m.update_gso_blocked(mode)
+                dt = time.perf_counter() - t
+                rec = dict(d=d, n=n, batch=B, gram_mode=mode, seconds=dt, GBps=B * by / dt / 1e9, ok=bool(ok.all()))
+                print("M2-blocked", json.dumps(rec), flush=True)
+                m.close()
     # ---- M3 ----
     for B in (64, 256, 1024, 5920):
         d = n = 60
