@@ -64,7 +64,19 @@ def hlll_fixtures():
     np.savez_compressed(os.path.join(HERE, "hlll_long.npz"), **pack)
 
 
+def svp_kat_fixture():
+    # --- the reference's SVP known-answer pair (tests/test_svp.cpp:373-374): input basis and a shortest vector -------
+    import re
+    src = "/root/reference/tests/lattices/"
+    rows = re.findall(r"\[([^\[\]]*)\]", open(src + "example_svp_in").read())
+    b = np.array([[int(x) for x in r.split()] for r in rows if r.strip()], dtype=np.int64)
+    sv = np.array([int(x) for x in re.findall(r"-?\d+", open(src + "example_svp_out").read())], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "example_svp.npz"), b_in=b, sv=sv)
+
+
 def main():
+    if '--only-svp' in sys.argv:
+        return svp_kat_fixture()
     if '--only-bkz' in sys.argv:
         return bkz_fixtures()
     if '--only-hlll' in sys.argv:
@@ -165,6 +177,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "leech_lll.npz"), b=np.array(O.read_matrix(lo), dtype=np.int64))
     bkz_fixtures()
     hlll_fixtures()
+    svp_kat_fixture()
     print("golden fixtures written to", HERE)
 
 

@@ -124,3 +124,23 @@ def test_two_devices_in_one_process_visit_the_same_nodes(en):
         res = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True, devices=[0, 1])
         assert res["stats"]["n_devices"] == 2
         assert np.array_equal(res["nodes"], ref["nodes"])
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_EXPERIMENTAL"),
+                    reason="added after the round's GPU budget was spent: set B200_TEST_EXPERIMENTAL=1")
+def test_reference_svp_known_answer_on_device(en):
+    """tests/test_svp.cpp:373-374 end to end on the device: device LLL, device enumeration with radius |b_0|^2, squared
+    norm of the result equals that of lattices/example_svp_out."""
+    import fplll_b200 as fb
+    z = H.gold("example_svp.npz")
+    want = int((z["sv"].astype(object) ** 2).sum())
+    b = z["b_in"].copy()
+    assert fb.lll_reduction(b, 0.99, 0.51) == 0
+    d = b.shape[0]
+    mut, rdiag = gso_block(b, 0, d)
+    res = en.enumerate_svp(mut, rdiag, None, float(rdiag[0]))
+    best = int((b[0].astype(object) ** 2).sum())
+    if res["solutions"]:
+        v = np.rint(res["solutions"][-1][1]).astype(np.int64) @ b
+        best = min(best, int((v.astype(object) ** 2).sum()))
+    assert best == want

@@ -35,3 +35,21 @@ def test_leech_kissing_number():
     res = O.enum_svp(mut, rdiag, None, 32.5, shrink=False)
     assert res["nsols"] == 196560 // 2  # +-v counted once (SVP symmetry break, enumerate_base.h:145-171)
     assert abs(res["best"] - 32.0) < 1e-9
+
+
+def test_reference_svp_known_answer():
+    """tests/test_svp.cpp:54-100,373-374: after LLL, the shortest vector of lattices/example_svp_in has the squared norm
+    of lattices/example_svp_out.  Oracle LLL + oracle enumeration (radius = |b_0|^2, as shortest_vector does)."""
+    z = H.gold("example_svp.npz")
+    want = int((z["sv"].astype(object) ** 2).sum())
+    m = O.OracleGSO(z["b_in"])
+    assert m.lll(0.99, 0.51)["status"] == 0
+    b = m.state()["b"]
+    d = b.shape[0]
+    mut, rdiag = gso_block(b, 0, d)
+    res = O.enum_svp(mut, rdiag, None, float(rdiag[0]), shrink=True)
+    best = int((b[0].astype(object) ** 2).sum())
+    if res["nsols"]:
+        v = np.rint(res["sol"]).astype(np.int64) @ b
+        best = min(best, int((v.astype(object) ** 2).sum()))
+    assert best == want
