@@ -503,7 +503,10 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   for (const void *f : fns)
     CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   if (b200gso_lll_warp_attrs(h->smem_bytes) || b200gso_lll_cta_attrs(d, n))
+  {
+    b200gso_destroy(h);
     return B200GSO_ECUDA;
+  }
   CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
   CK(cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream));
   CK(cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream));
