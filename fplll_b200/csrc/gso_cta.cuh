@@ -29,13 +29,17 @@
 #ifndef B200_MU_CACHE
 #define B200_MU_CACHE 0
 #endif
+// Same status for the CTA-wide move_row (cta_move_row below): -DB200_CTA_MOVE=1 compiles it in.
+#ifndef B200_CTA_MOVE
+#define B200_CTA_MOVE 0
+#endif
 
 namespace b200 {
 
 constexpr int CTA_WARPS = 8;
 constexpr int CTA_OWN   = 2;  // panels a warp can own: 16 panels = d <= 512
 
-enum { COOP_EXIT = 0, COOP_UPDATE = 1, COOP_BACKSUB = 2, COOP_IGEMV = 3, COOP_MULOAD = 4 };
+enum { COOP_EXIT = 0, COOP_UPDATE = 1, COOP_BACKSUB = 2, COOP_IGEMV = 3, COOP_MULOAD = 4, COOP_MOVE = 5 };
 
 struct CoopShared
 {
@@ -478,6 +482,93 @@ __device__ inline void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lan
 
 #endif
 
+#if B200_CTA_MOVE
+// ---- MOVE -----------------------------------------------------------------------------------------------------------
+// move_row(old_r, new_r) (gso.cpp:289-366) by the whole CTA: warp_move_row (gso_warp.cuh) with its lane-strided passes
+// (one column of mu / r / b / bf per lane, one Gram row per lane) strided over all CTA_WARPS * 32 threads instead; the
+// data movement per element is the same, only who carries it differs.
+__device__ inline void cta_move_row(CoopShared &C, int old_r, int new_r, int w, int lane)
+{
+  const View &v = C.v;
+  const int tid = threadIdx.x, NT = CTA_WARPS * 32;
+  if (old_r == new_r)
+  {
+    cta_bar(2);
+    return;
+  }
+  const int nkr    = v.meta[M_NKR];
+  const bool right = new_r < old_r;
+  const int lo = right ? new_r : old_r, hi = right ? old_r : new_r;
+  cta_bar(2);  // everybody has read nkr and the old validity before anybody lowers it
+  for (int i = lo + tid; i < nkr; i += NT)
+    v.valid[i] = min(v.valid[i], lo);
+  if (tid == 0)
+  {
+    v.meta[M_CLEAN_SR]  = min(v.meta[M_CLEAN_SR], lo);
+    v.meta[M_CLEAN_LLL] = min(v.meta[M_CLEAN_LLL], lo);
+  }
+  for (int k = tid; k < lo; k += NT)
+  {
+    rotate_seq<double>([&](int i) -> double & { return v.mu[mu_off(i, k)]; }, lo, hi, right);
+    rotate_seq<double>([&](int i) -> double & { return v.r[tri_off(i) + k]; }, lo, hi, right);
+  }
+  for (int c = tid; c < v.n; c += NT)
+  {
+    rotate_seq<int64_t>([&](int i) -> int64_t & { return v.b[(size_t)i * v.ldb + c]; }, lo, hi, right);
+    rotate_seq<double>([&](int i) -> double & { return v.bf[bf_off(i, c, v.n)]; }, lo, hi, right);
+  }
+  const int ghi      = right ? hi : min(hi, nkr - 1);
+  const bool do_gram = right || lo < nkr - 1;
+  const size_t beg   = tri_off(lo), end = do_gram ? tri_off(ghi + 1) : beg;
+  if (do_gram)
+  {
+    for (int i = ghi + 1 + tid; i < nkr; i += NT)
+    {
+      double *row = v.gf + tri_off(i);
+      rotate_seq<double>([&](int j) -> double & { return row[j]; }, lo, ghi, right);
+    }
+    for (size_t t = beg + tid; t < end; t += NT)
+      v.scratch[t - beg] = v.gf[t];
+  }
+  cta_bar(2);  // scratch copy complete
+  if (do_gram)
+  {
+    // the rotated rows, rebuilt from the scratch copy: new(i,j) = old_sym(s(i), s(j)); (row, column) pairs over the CTA
+    for (int i = lo + w; i <= ghi; i += CTA_WARPS)
+    {
+      const int si = right ? (i == lo ? ghi : i - 1) : (i == ghi ? lo : i + 1);
+      for (int j = lane; j <= i; j += 32)
+      {
+        int sj = j;
+        if (j >= lo)
+          sj = right ? (j == lo ? ghi : j - 1) : (j == ghi ? lo : j + 1);
+        const int a = max(si, sj), b = min(si, sj);
+        v.gf[tri_off(i) + j] = v.scratch[tri_off(a) + b - beg];
+      }
+    }
+  }
+  cta_bar(2);  // validity minima above are complete before the per-row metadata rotates
+  if (tid == 0)
+    rotate_seq<int>([&](int i) -> int & { return v.valid[i]; }, lo, hi, right);
+  else if (tid == 32)
+    rotate_seq<int>([&](int i) -> int & { return v.row_expo[i]; }, lo, hi, right);
+  else if (tid == 64 && !right && new_r >= nkr)
+    rotate_seq<int>([&](int i) -> int & { return v.irs[i]; }, lo, hi, false);
+  cta_bar(2);
+  if (!right && new_r >= nkr && old_r < nkr && w == 0)
+  {
+    const int nz = size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
+    if (lane == 0)
+    {
+      v.meta[M_NKR] = nkr - 1;
+      v.meta[M_NSR] = nkr - 1;
+      v.irs[new_r]  = max(nz, 1);
+    }
+  }
+  cta_bar(2);
+}
+#endif
+
 // helper warps: wait for commands until the master says EXIT
 __device__ inline void coop_helper_loop(CoopShared &C, int w, int lane)
 {
@@ -496,6 +587,10 @@ __device__ inline void coop_helper_loop(CoopShared &C, int w, int lane)
 #if B200_MU_CACHE
     else if (cmd == COOP_MULOAD)
       cta_mu_load(C, a0, a1, w, lane);
+#endif
+#if B200_CTA_MOVE
+    else if (cmd == COOP_MOVE)
+      cta_move_row(C, a0, a1, w, lane);
 #endif
   }
 }
@@ -550,6 +645,19 @@ template <bool COOP> __device__ inline void lll_mu_refresh_diag(CoopShared *C, i
   __syncwarp();
 }
 
+#endif
+
+#if B200_CTA_MOVE
+template <bool COOP> __device__ inline void lll_move_row(const View &v, int old_r, int new_r, int lane, CoopShared *C)
+{
+  if (!COOP)
+  {
+    warp_move_row(v, old_r, new_r, lane);
+    return;
+  }
+  coop_post(C, COOP_MOVE, old_r, new_r, 0, lane);
+  cta_move_row(*C, old_r, new_r, 0, lane);
+}
 #endif
 
 }  // namespace b200

@@ -11,6 +11,11 @@
 namespace b200 {
 
 // mu(i,k) as the LLL code reads it: through the CTA's shared-memory cache when that is compiled in (gso_cta.cuh)
+#if B200_CTA_MOVE
+#define LLL_MOVE_ROW(old_, new_) lll_move_row<COOP>(v, (old_), (new_), lane, C)
+#else
+#define LLL_MOVE_ROW(old_, new_) warp_move_row(v, (old_), (new_), lane)
+#endif
 #if B200_MU_CACHE
 #define LLL_MU_LOAD(i_, k_) (COOP ? coop_mu_load(*C, (i_), (k_)) : v.mu[mu_off((i_), (k_))])
 #define LLL_MU_RELOAD(lo_, hi_) lll_mu_reload<COOP>(C, (lo_), (hi_), lane)
@@ -397,7 +402,7 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
   __syncwarp();
   for (; zeros < d && warp_b_row_is_zero(v, 0, lane); zeros++)
   {
-    warp_move_row(v, kappa_min, kappa_end - 1 - zeros, lane);
+    LLL_MOVE_ROW(kappa_min, kappa_end - 1 - zeros);
     LLL_MU_RELOAD(kappa_min, kappa_end - 1 - zeros);
   }
   if (zeros < d)
@@ -492,14 +497,14 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
       const int old_k = kappa;
       if (action == 1)
       {
-        warp_move_row(v, old_k, new_kappa, lane);
+        LLL_MOVE_ROW(old_k, new_kappa);
         LLL_MU_RELOAD(new_kappa, old_k);
         kappa = new_kappa;
       }
       else
       {
         zeros++;
-        warp_move_row(v, old_k, kappa_end - zeros, lane);
+        LLL_MOVE_ROW(old_k, kappa_end - zeros);
         LLL_MU_RELOAD(old_k, kappa_end - zeros);
         kappa = old_k;
         continue;
