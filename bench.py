@@ -165,10 +165,7 @@ def hh_extras(local):
         T = i * n - i * (i - 1) // 2
         per = 8 * (T + 2 * n)
         peak, _ = peaks()
-        if os.environ.get("B200_HH_CTA32"):
-            out_variant = "hk_update_R_cta32 (experimental, B200_HH_CTA32=1)"
-        else:
-            out_variant = "hk_update_R"
+        out_variant = "hk_update_R"
         out = {"workload": "batched update_R(399, false) on %d lattices of d=n=400 (V zero-filled: timing only)" % B,
                "kernel": out_variant,
                "algorithmic_bytes_per_lattice": per, "ms_per_launch": ms, "GBps": B * per / (ms * 1e-3) / 1e9,

@@ -13,7 +13,7 @@ class B200Error(RuntimeError):
 def load(name):
     if name in _cache:
         return _cache[name]
-    path = os.path.join(HERE, "lib", name)
+    path = os.path.join(HERE, os.environ.get("B200_LIB_DIR", "lib"), name)
     if not os.path.exists(path):
         raise B200Error("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(the product path has no CPU fallback)" % path)

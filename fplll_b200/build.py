@@ -5,7 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# B200_LIB_DIR: build/load a variant (other -D flags) next to the default one; the default is what ships
+LIBDIR = os.path.join(HERE, os.environ.get("B200_LIB_DIR", "lib"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               # the reference build never contracts a*b+c (configure.ac:25: -O3, no -march): bit parity needs the same
               "--fmad=false", "-Xcompiler", "-fPIC", "-shared"]
@@ -18,11 +19,25 @@ TARGETS = {
 }
 
 
+def _deps(src, seen=None):
+    """The unit's own quoted #include closure (csrc/*.cuh and include/*.h): an edit rebuilds only the units that see it."""
+    import re
+    seen = set() if seen is None else seen
+    src = os.path.normpath(src)
+    if src in seen or not os.path.exists(src):
+        return seen
+    seen.add(src)
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(src).read(), flags=re.M):
+        _deps(os.path.join(os.path.dirname(src), inc), seen)
+    return seen
+
+
 def _stale(out, srcs):
     if not os.path.exists(out):
         return True
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", f)
-                                                                  for f in os.listdir(os.path.join(HERE, "..", "include"))]
+    deps = set()
+    for s in srcs:
+        _deps(s, deps)
     return any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps)
 
 

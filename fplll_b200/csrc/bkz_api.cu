@@ -93,8 +93,10 @@ public:
     st->sec_lll += dt;
     st->lll_calls++;
 #ifdef B200_LLL_PROFILE
+    long pc[8];
+    b200gso_lll_profile(pc);
     for (int q = 0; q < 8; q++)
-      prof_cyc[q] += stats[4 + q];
+      prof_cyc[q] += pc[q];
     prof_lll_sec += dt;
     prof_swaps += stats[0], prof_iters += stats[3];
 #endif
@@ -445,7 +447,15 @@ public:
       if (kappa_max < kappa && clean)
         kappa_max = kappa;
     }
-    size_reduction(max_row - 1, max_row, max_row - 2);  // bkz.cpp:436-438
+    {
+      // bkz.cpp:436-438: the reference calls lll_obj.size_reduction here and IGNORES its return value (a Babai failure
+      // at this point does not abort the tour)
+      const double t0 = now_s();
+      int status      = 0;
+      GCK(b200gso_size_reduction(g, 0.51, max_row - 1, max_row, max_row - 2, &status));
+      st->sec_lll += now_s() - t0;
+      st->sizered_calls++;
+    }
     return clean;
   }
 
@@ -617,28 +627,30 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
   {
     GCK(b200gso_set_basis(g, b));
     Driver drv(h, g, d, *param, stats);
-    if (!(param->flags & B200BKZ_NO_LLL))
-    {
-      // the reference runs its wrapper LLL here (bkz.cpp:869-876); in the int64 regime that is LLL(delta, 0.51)
-      long swaps;
-      drv.lll(0, 0, d, &swaps);
-    }
-    else
-    {
-      int ok = 1;
-      GCK(b200gso_update_gso(g, &ok));
-    }
-    stats->slope_before = drv.current_slope(0, d);
-    {
-      double m;
-      long e;
-      drv.r_exp(0, m, e);
-      stats->r00_before = ldexp(m, (int)e);
-    }
-    stats->sec_lll = 0, stats->lll_calls = 0;
-    const double tb = now_s();
+    double tb = now_s();
     try
     {
+      if (!(param->flags & B200BKZ_NO_LLL))
+      {
+        // the reference runs its wrapper LLL here (bkz.cpp:869-876); in the int64 regime that is LLL(delta, 0.51).
+        // A failure of this LLL (RED_BABAI_FAILURE on an fp64-fragile basis) is the call's status, not an exception.
+        long swaps;
+        drv.lll(0, 0, d, &swaps);
+      }
+      else
+      {
+        int ok = 1;
+        GCK(b200gso_update_gso(g, &ok));
+      }
+      stats->slope_before = drv.current_slope(0, d);
+      {
+        double m;
+        long e;
+        drv.r_exp(0, m, e);
+        stats->r00_before = ldexp(m, (int)e);
+      }
+      stats->sec_lll = 0, stats->lll_calls = 0;
+      tb            = now_s();
       stats->status = drv.bkz();
     }
     catch (RedFailure &f)
@@ -655,6 +667,15 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
                     "%.3g cycles; size_reduction calls %.1f s wall\n",
             (double)drv.prof_cyc[4], (double)drv.prof_cyc[5], (double)drv.prof_cyc[6], (double)drv.prof_cyc[7],
             drv.prof_sr_sec);
+    {
+      long long cp[32];
+      b200gso_lll_cta_profile(cp);
+      fprintf(stderr, "  CTA ops (all LLL + size-reduction calls): update calls %lld (mean i %.1f, wavefront steps %lld, Gram entries "
+                      "%lld): Gram+prefix %.3g, wavefront %.3g, diagonal %.3g cycles; back-substitutions %lld (steps %lld) %.3g "
+                      "cycles; integer-row calls %lld (rows %lld) %.3g cycles\n",
+              cp[0], cp[0] ? (double)cp[12] / cp[0] : 0.0, cp[1], cp[13], (double)cp[2], (double)cp[3], (double)cp[4], cp[5],
+              cp[6], (double)cp[7], cp[9], cp[10], (double)cp[11]);
+    }
 #endif
     stats->sec_other = stats->sec_total - stats->sec_enum - stats->sec_lll;
     if (stats->status == 0 || stats->status == B200_RED_BKZ_LOOPS_LIMIT || stats->status == B200_RED_BKZ_TIME_LIMIT)
@@ -670,6 +691,11 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
   catch (std::exception &ex)
   {
     g_bkz_err = ex.what();
+    ret       = B200BKZ_ECUDA;
+  }
+  catch (...)  // nothing may cross the C boundary
+  {
+    g_bkz_err = "b200bkz_reduce: unknown C++ exception";
     ret       = B200BKZ_ECUDA;
   }
   (void)t0;

@@ -20,10 +20,22 @@ namespace {
 
 int g_ngpus = 1;
 
+struct Callbacks
+{
+  std::function<fplll::extenum_cb_process_sol> *sol;
+  std::function<fplll::extenum_cb_process_subsol> *subsol;
+};
+
 double trampoline(void *ctx, double dist, const double *sol)
 {
-  auto *f = static_cast<std::function<fplll::extenum_cb_process_sol> *>(ctx);
-  return (*f)(dist, const_cast<double *>(sol));  // extenum_cb_process_sol returns the new bound (enumerate_ext_api.h:62)
+  auto *c = static_cast<Callbacks *>(ctx);
+  return (*c->sol)(dist, const_cast<double *>(sol));  // extenum_cb_process_sol returns the new bound (enumerate_ext_api.h:62)
+}
+
+void sub_trampoline(void *ctx, double dist, const double *subsol, int offset)
+{
+  auto *c = static_cast<Callbacks *>(ctx);
+  (*c->subsol)(dist, const_cast<double *>(subsol), offset);  // enumerate_ext_api.h:70-71
 }
 
 }  // namespace
@@ -32,13 +44,13 @@ double trampoline(void *ctx, double dist, const double *sol)
 std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM>
 b200_enumerate(const int dim, fplll::enumf maxdist, std::function<fplll::extenum_cb_set_config> cbfunc,
                std::function<fplll::extenum_cb_process_sol> cbsol,
-               std::function<fplll::extenum_cb_process_subsol> /*cbsubsol*/, bool dual, bool findsubsols)
+               std::function<fplll::extenum_cb_process_subsol> cbsubsol, bool dual, bool findsubsols)
 {
   std::array<uint64_t, FPLLL_EXTENUM_MAX_EXTENUM_DIM> ret{};
-  if (dual || findsubsols || dim < 2 || dim > B200ENUM_MAX_DIM)
+  if (dim < 2 || dim > B200ENUM_MAX_DIM)
   {
-    ret[0] = ~uint64_t(0);  // "not supported": fplll uses its own enumerator (enumerate_ext.cpp:88), as enumlib does
-    return ret;
+    ret[0] = ~uint64_t(0);  // "not supported": fplll uses its own enumerator (enumerate_ext.cpp:88); dual and
+    return ret;             // sub-solution requests ARE served (enumlib declines dual, enumlib.cpp:98-104)
   }
   std::vector<double> mut((size_t)dim * dim, 0.0), rdiag(dim), pruning(dim);
   cbfunc(mut.data(), dim, /*mutranspose=*/true, rdiag.data(), pruning.data());
@@ -46,8 +58,10 @@ b200_enumerate(const int dim, fplll::enumf maxdist, std::function<fplll::extenum
   for (int i = 0; i < g_ngpus; i++)
     devs[i] = i;
   std::vector<uint64_t> nodes(dim, 0);
-  const int rc = b200enum_run(dim, maxdist, mut.data(), rdiag.data(), pruning.data(), 0, devs.data(), g_ngpus, 0, 1,
-                              trampoline, &cbsol, nodes.data(), nullptr);
+  Callbacks cbs{&cbsol, &cbsubsol};
+  const int flags = (dual ? B200ENUM_DUAL : 0) | (findsubsols ? B200ENUM_FINDSUBSOLS : 0);
+  const int rc    = b200enum_run_ex(dim, maxdist, mut.data(), rdiag.data(), pruning.data(), flags, devs.data(), g_ngpus,
+                                    0, 1, trampoline, findsubsols ? sub_trampoline : nullptr, &cbs, nodes.data(), nullptr);
   if (rc != B200ENUM_OK)  // a broken GPU must not silently turn into a CPU enumeration
     throw std::runtime_error(std::string("b200_enumerate: ") + b200enum_last_error());
   for (int i = 0; i < dim; i++)

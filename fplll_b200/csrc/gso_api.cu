@@ -9,6 +9,7 @@
 #include "gso_tma.cuh"
 
 thread_local std::string b200gso_g_err;
+long b200gso_g_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
 
@@ -392,11 +393,11 @@ static void launch_update_row(b200gso *h, int i, int last_j)
     k_update_row_tma<<<g, t, sm, h->stream>>>(h->S, i, last_j, h->d_ok);
     return;
   }
-  switch (upd_variant())
+  switch (upd_variant())  // unknown values take <5>, here and in b200gso_resident_lattices
   {
-  case 5: k_update_row<5><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
+  case 8: k_update_row<8><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
   case 6: k_update_row<6><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
-  default: k_update_row<8><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
+  default: k_update_row<5><<<g, t, h->smem_compact, h->stream>>>(h->S, i, last_j, h->d_ok); break;
   }
 }
 
@@ -476,9 +477,11 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   rc |= dev_alloc(h, &h->d_rows, (size_t)batch * n);
   rc |= dev_alloc(h, &h->d_rowbuf, (size_t)2 * batch * d);
   rc |= dev_alloc(h, &h->d_valid_i, (size_t)batch);
-  rc |= dev_alloc(h, &h->d_stats, (size_t)batch * 4 + 8);
+  rc |= dev_alloc(h, &h->d_stats, (size_t)batch * 4 + 8 + ((size_t)batch + 1) / 2);  // + status ints behind the longs
   rc |= dev_alloc(h, &h->d_blk, (size_t)d * d + 4 * (size_t)d + 16);
   h->d_ops = nullptr, h->ops_cap = 0;
+  h->h_pin = nullptr, h->pin_bytes = 0, h->h_ops = nullptr, h->h_ops_cap = 0;
+  h->stream = nullptr;
   if (rc)
   {
     for (void *p : h->allocs)
@@ -486,7 +489,22 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
     delete h;
     return B200GSO_ENOMEM;
   }
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    g_err = "b200gso_create: cudaStreamCreate failed";
+    h->stream = nullptr;
+    b200gso_destroy(h);
+    return B200GSO_ECUDA;
+  }
+  h->pin_bytes = ((size_t)d * d + 4 * (size_t)d + 64) * sizeof(double) + ((size_t)batch * 4 + 8) * sizeof(long) +
+                 (size_t)batch * sizeof(int);
+  if (cudaMallocHost(&h->h_pin, h->pin_bytes) != cudaSuccess)
+  {
+    g_err = "b200gso_create: cudaMallocHost failed";
+    h->h_pin = nullptr;
+    b200gso_destroy(h);
+    return B200GSO_ENOMEM;
+  }
   h->smem_bytes = WARPS_PER_CTA * (WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1) + ((MetaCache::ints(d) + 1) >> 1)) *
                   sizeof(double);
   h->smem_compact = WARPS_PER_CTA * WarpSmem::doubles(d, n, false) * sizeof(double);
@@ -500,19 +518,35 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
                        (const void *)k_apply_ops};
+  // The kernels are process-wide: the attribute is the opt-in maximum (227 KB), never this handle's own size — a
+  // second, smaller handle must not lower the limit under a larger live one.
   for (const void *f : fns)
-    CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  {
+    const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN_MAX);
+    if (e != cudaSuccess)
+    {
+      g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+      b200gso_destroy(h);
+      return B200GSO_ECUDA;
+    }
+  }
   if (b200gso_lll_warp_attrs(h->smem_bytes) || b200gso_lll_cta_attrs(d, n))
   {
     b200gso_destroy(h);
     return B200GSO_ECUDA;
   }
-  CK(cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream));
-  CK(cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(S.gf, 0, S.tri_stride * batch * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(S.meta, 0, (size_t)M_STRIDE * batch * sizeof(int), h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  cudaError_t me = cudaMemsetAsync(S.b, 0, S.b_stride * batch * sizeof(int64_t), h->stream);
+  if (me == cudaSuccess) me = cudaMemsetAsync(S.mu, 0, S.mu_stride * batch * sizeof(double), h->stream);
+  if (me == cudaSuccess) me = cudaMemsetAsync(S.r, 0, S.tri_stride * batch * sizeof(double), h->stream);
+  if (me == cudaSuccess) me = cudaMemsetAsync(S.gf, 0, S.tri_stride * batch * sizeof(double), h->stream);
+  if (me == cudaSuccess) me = cudaMemsetAsync(S.meta, 0, (size_t)M_STRIDE * batch * sizeof(int), h->stream);
+  if (me == cudaSuccess) me = cudaStreamSynchronize(h->stream);
+  if (me != cudaSuccess)
+  {
+    g_err = std::string("b200gso_create: ") + cudaGetErrorString(me);
+    b200gso_destroy(h);
+    return B200GSO_ECUDA;
+  }
   *out = h;
   return 0;
 }
@@ -531,6 +565,10 @@ void b200gso_destroy(b200gso_t *h)
     cudaFree(p);
   if (h->d_ops)
     cudaFree(h->d_ops);
+  if (h->h_pin)
+    cudaFreeHost(h->h_pin);
+  if (h->h_ops)
+    cudaFreeHost(h->h_ops);
   delete h;
 }
 
@@ -808,43 +846,31 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
     g_err = "b200gso_lll/size_reduction: bad range (or d > 512)";
     return B200GSO_EINVAL;
   }
-  int *d_st     = h->d_ok;
-  long *d_stats = stats ? h->d_stats : nullptr;  // preallocated: stream-ordered allocation would hand its memory back
-                                                 // to the driver at every synchronisation and cost milliseconds
+  // status ints live right behind the statistics longs: one D2H copy into pinned memory brings back both
+  long *d_stats = h->d_stats;
+  int *d_st     = (int *)(h->d_stats + 4 * (size_t)S.B + 8);
   // few lattices (BKZ works on one): a whole CTA per lattice (k_lll_cta); many: one warp per lattice, the batch hides
   // the latencies.  B200_LLL_CTA=0 forces the one-warp kernels, B200_LLL_CTA_MAX moves the switch-over.
-  const int cta_on  = getenv("B200_LLL_CTA") ? atoi(getenv("B200_LLL_CTA")) : 1;
-  const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
-  if (cta_on && S.B <= cta_max && S.d > 32)
+  static const int cta_on  = getenv("B200_LLL_CTA") ? atoi(getenv("B200_LLL_CTA")) : 1;
+  static const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
+  const bool cta = cta_on && S.B <= cta_max && S.d > 32;
+  if (cta)
   {
-    if (b200gso_lll_cta_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, (stats && mode == 0) ? h->d_stats : nullptr))
+    if (b200gso_lll_cta_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, (stats && mode == 0) ? d_stats : nullptr))
       return B200GSO_ECUDA;
-    CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
-    if (stats)
-    {
-#ifdef B200_LLL_PROFILE
-      CK(cudaMemcpyAsync(stats, h->d_stats, sizeof(long) * (4 * S.B + 8), cudaMemcpyDeviceToHost, h->stream));
-#else
-      CK(cudaMemcpyAsync(stats, h->d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
-#endif
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaGetLastError());
-    return 0;
   }
-  if (b200gso_lll_warp_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, d_stats))
+  else if (b200gso_lll_warp_launch(h, mode, delta, eta, kmin, kstart, kend, sr_start, d_st, stats ? d_stats : nullptr))
     return B200GSO_ECUDA;
-  CK(cudaMemcpyAsync(status, d_st, sizeof(int) * S.B, cudaMemcpyDeviceToHost, h->stream));
-  if (stats)
-  {
-#ifdef B200_LLL_PROFILE
-    CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * (4 * S.B + 4), cudaMemcpyDeviceToHost, h->stream));
-#else
-    CK(cudaMemcpyAsync(stats, d_stats, sizeof(long) * 4 * S.B, cudaMemcpyDeviceToHost, h->stream));
-#endif
-  }
+  const size_t nl = 4 * (size_t)S.B + 8, bytes = nl * sizeof(long) + (size_t)S.B * sizeof(int);
+  CK(cudaMemcpyAsync(h->h_pin, d_stats, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
+  memcpy(status, h->h_pin + nl * sizeof(long), (size_t)S.B * sizeof(int));
+  if (stats)
+    memcpy(stats, h->h_pin, 4 * (size_t)S.B * sizeof(long));  // `stats` is batch*4 longs for the caller, always
+#ifdef B200_LLL_PROFILE
+  memcpy(b200gso_g_prof, h->h_pin + 4 * (size_t)S.B * sizeof(long), 8 * sizeof(long));
+#endif
   return 0;
 }
 
@@ -901,10 +927,20 @@ int b200gso_apply_ops(b200gso_t *h, const b200gso_op *ops, int n)
     h->ops_cap = std::max<size_t>(1024, (size_t)n * 2);
     CK(cudaMalloc(&h->d_ops, sizeof(b200gso_op) * h->ops_cap));
   }
+  if ((size_t)n > h->h_ops_cap)
+  {
+    if (h->h_ops)
+      cudaFreeHost(h->h_ops);
+    h->h_ops     = nullptr;
+    h->h_ops_cap = 0;
+    CK(cudaMallocHost(&h->h_ops, sizeof(b200gso_op) * std::max<size_t>(1024, (size_t)n * 2)));
+    h->h_ops_cap = std::max<size_t>(1024, (size_t)n * 2);
+  }
+  memcpy(h->h_ops, ops, sizeof(b200gso_op) * n);  // pinned copy: the caller's array is free on return
   b200gso_op *d_ops = h->d_ops;
-  CK(cudaMemcpyAsync(d_ops, ops, sizeof(b200gso_op) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_ops, h->h_ops, sizeof(b200gso_op) * n, cudaMemcpyHostToDevice, h->stream));
   k_apply_ops<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, d_ops, n);
-  CK(cudaStreamSynchronize(h->stream));  // `ops` is caller memory
+  CK(cudaStreamSynchronize(h->stream));  // the next call reuses the staging buffer
   CK(cudaGetLastError());
   return 0;
 }
@@ -934,11 +970,14 @@ int b200gso_get_block(b200gso_t *h, int lattice, int first, int beta, double *mu
   const size_t nd = (size_t)beta * beta + beta;
   long *te        = (long *)(t + nd);
   k_get_block<<<1, 256, 0, h->stream>>>(h->S, lattice, first, beta, t, t + (size_t)beta * beta, te);
-  CK(cudaMemcpyAsync(mut, t, (size_t)beta * beta * 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(r_mant, t + (size_t)beta * beta, beta * 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(r_expo, te, beta * sizeof(long), cudaMemcpyDeviceToHost, h->stream));
+  // mut | r_mant | r_expo are contiguous on the device: one copy into pinned memory, scattered on the host
+  const size_t bytes = nd * 8 + (size_t)beta * sizeof(long);
+  CK(cudaMemcpyAsync(h->h_pin, t, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
+  memcpy(mut, h->h_pin, (size_t)beta * beta * 8);
+  memcpy(r_mant, h->h_pin + (size_t)beta * beta * 8, (size_t)beta * 8);
+  memcpy(r_expo, h->h_pin + nd * 8, (size_t)beta * sizeof(long));
   return 0;
 }
 
@@ -947,7 +986,18 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
   if (!h || reps <= 0 || i < 0 || i >= h->S.d)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  std::vector<cudaEvent_t> ev(2 * (size_t)reps + 2);
+  struct Events  // released on every exit path
+  {
+    std::vector<cudaEvent_t> v;
+    ~Events()
+    {
+      for (cudaEvent_t e : v)
+        if (e)
+          cudaEventDestroy(e);
+    }
+  } evs;
+  evs.v.assign(2 * (size_t)reps + 2, nullptr);
+  std::vector<cudaEvent_t> &ev = evs.v;
   for (auto &e : ev)
     CK(cudaEventCreate(&e));
   CK(cudaEventRecord(ev[2 * reps], h->stream));
@@ -972,8 +1022,6 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
   }
   float all = 0;
   CK(cudaEventElapsedTime(&all, ev[2 * reps], ev[2 * reps + 1]));
-  for (auto &e : ev)
-    cudaEventDestroy(e);
   if (ms_update_mean)
     *ms_update_mean = (float)(tot / reps);
   if (ms_total)
@@ -994,6 +1042,22 @@ int b200gso_resident_lattices(b200gso_t *h)
     return B200GSO_ECUDA;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   return nb * sms * WARPS_PER_CTA;
+}
+
+int b200gso_lll_profile(long *out8)
+{
+  if (!out8)
+    return B200GSO_EINVAL;
+  for (int q = 0; q < 8; q++)
+    out8[q] = b200gso_g_prof[q];
+  return 0;
+}
+
+int b200gso_lll_cta_profile(long long *out32)
+{
+  if (!out32)
+    return B200GSO_EINVAL;
+  return b200gso_lll_cta_prof(out32);
 }
 
 int b200gso_sync(b200gso_t *h)

@@ -18,6 +18,10 @@ extern thread_local std::string b200gso_g_err;  // defined in gso_api.cu
 #define g_err b200gso_g_err
 
 constexpr int WARPS_PER_CTA = 4;
+// opt-in maximum of dynamic shared memory per CTA on sm_100: what every kernel's MaxDynamicSharedMemorySize is set to
+constexpr int SMEM_OPTIN_MAX = 227 * 1024;
+// -DB200_LLL_PROFILE builds: device-clock phase counters of the last LLL call (b200gso_lll_profile reads them)
+extern long b200gso_g_prof[8];
 
 #define CK(call)                                                                                   \
   do                                                                                               \
@@ -118,6 +122,12 @@ struct b200gso
   double *d_blk;      // d*d + 2*d doubles + d longs (get_block / get_r_diag staging)
   b200gso_op *d_ops;  // op-list staging (grown on demand)
   size_t ops_cap;
+  // pinned host staging for the single-lattice driver calls (BKZ: ~10^5 small synchronous calls per tour — every
+  // pageable copy costs a driver-side bounce, so results travel in ONE copy into pinned memory and are scattered here)
+  unsigned char *h_pin;
+  size_t pin_bytes;
+  b200gso_op *h_ops;
+  size_t h_ops_cap;
   std::vector<void *> allocs;
 };
 
@@ -128,5 +138,6 @@ int b200gso_lll_warp_attrs(size_t smem_bytes);
 int b200gso_lll_warp_launch(b200gso *h, int mode, double delta, double eta, int kmin, int kstart, int kend,
                             int sr_start, int *d_st, long *d_stats);
 int b200gso_lll_cta_attrs(int d, int n);
+int b200gso_lll_cta_prof(long long *out32);
 int b200gso_lll_cta_launch(b200gso *h, int mode, double delta, double eta, int kmin, int kstart, int kend, int sr_start,
                            int *d_st, long *d_stats);

@@ -23,18 +23,42 @@
 #pragma once
 #include "gso_warp.cuh"
 
-// Compile-time switch for the shared-memory cache of the leading mu panels (see CoopShared::mu_s).  Written at the end
-// of round 1 without GPU time left to measure it, so it is compiled OUT by default: build with -DB200_MU_CACHE=1 and run
-// with B200_LLL_MU_SMEM=1 to try it.
+// Compile-time switches for the shared-memory cache of the leading mu panels (see CoopShared::mu_s; B200_LLL_MU_SMEM=0
+// turns it off at run time) and the CTA-wide move_row (cta_move_row below).  Both validated on hardware in round 2
+// (same LLL / BKZ trajectories; BKZ-60 tour: move_row -1.4 s, mu cache -1.0 s, gpurun_out/r2/bkz60_*.txt).
 #ifndef B200_MU_CACHE
-#define B200_MU_CACHE 0
+#define B200_MU_CACHE 1
 #endif
-// Same status for the CTA-wide move_row (cta_move_row below): -DB200_CTA_MOVE=1 compiles it in.
 #ifndef B200_CTA_MOVE
-#define B200_CTA_MOVE 0
+#define B200_CTA_MOVE 1
 #endif
 
 namespace b200 {
+
+// -DB200_LLL_PROFILE: device-clock counters of the cooperative operations (thread 0 of the one CTA BKZ runs), read back
+// by b200gso_lll_cta_prof: [0] update calls [1] wavefront steps [2] Gram+prefix cycles [3] wavefront cycles [4] diagonal
+// cycles [5] back-substitution calls [6] its steps [7] its cycles [9] integer-row calls [10] rows [11] cycles
+// [12] sum of i over update calls [13] Gram entries recomputed
+#ifdef B200_LLL_PROFILE
+static __device__ long long g_cta_prof[32];
+#define CTA_PT(var) const long long var = clock64()
+#define CTA_PADD(slot, t0)                      \
+  do                                            \
+  {                                             \
+    if (threadIdx.x == 0)                       \
+      g_cta_prof[slot] += clock64() - (t0);     \
+  } while (0)
+#define CTA_PCNT(slot, val)                     \
+  do                                            \
+  {                                             \
+    if (threadIdx.x == 0)                       \
+      g_cta_prof[slot] += (val);                \
+  } while (0)
+#else
+#define CTA_PT(var)
+#define CTA_PADD(slot, t0)
+#define CTA_PCNT(slot, val)
+#endif
 
 constexpr int CTA_WARPS = 8;
 constexpr int CTA_OWN   = 2;  // panels a warp can own: 16 panels = d <= 512
@@ -167,6 +191,10 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
   const int jl = min(last_j, i - 1);  // last off-diagonal column to produce
   const int p0 = j0 >> 5;
   const int pl = (jl >= j0) ? (jl >> 5) : p0 - 1;  // panels p0..pl carry work (none if only the diagonal is asked for)
+  CTA_PT(tp0_);
+  CTA_PCNT(0, 1);
+  CTA_PCNT(1, pl - p0 + 1);
+  CTA_PCNT(12, i);
 
   if (w == 0)
   {
@@ -199,6 +227,8 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
       {
         g        = lane_dot_deep(v.bf + bf_off(j, 0, n), s.vb, ncols);
         gfrow[j] = g;
+        if (threadIdx.x == 0)
+          CTA_PCNT(13, 32);
       }
       a = lane_chain<true>(g, coop_mu_panel(C, p) + lane, s.rrow, 0, 32 * p0);
     }
@@ -208,6 +238,8 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
   }
 
   bool ok = true;
+  CTA_PADD(2, tp0_);
+  CTA_PT(tp1_);
   for (int sp = p0; sp <= pl; ++sp)
   {
     const int ow = (sp - p0) % CTA_WARPS, ou = (sp - p0) / CTA_WARPS;
@@ -279,8 +311,10 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
   if (!ok)
     C.flag = 0;
   cta_bar(2);
+  CTA_PADD(3, tp1_);
   if (!C.flag)
     return false;
+  CTA_PT(tp2_);
 
   if (last_j >= i)
   {
@@ -315,6 +349,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
   if (tid == 0)
     v.valid[i] = last_j + 1;
   cta_bar(2);
+  CTA_PADD(4, tp2_);
   return true;
 }
 
@@ -328,6 +363,9 @@ __device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_
   const int ek  = v.row_expo[kappa];
   unsigned *xmask = (unsigned *)(s.xs + ((v.d + 1) & ~1));
   const int p_hi = (sr_end - 1) >> 5, p_lo = sr_start >> 5;
+  CTA_PT(tb0_);
+  CTA_PCNT(5, 1);
+  CTA_PCNT(6, p_hi - p_lo + 1);
   // panel q is owned by warp (p_hi - q) % CTA_WARPS, slot (p_hi - q) / CTA_WARPS
   double val[CTA_OWN];
 #pragma unroll
@@ -402,6 +440,7 @@ __device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_
       }
     }
   }
+  CTA_PADD(7, tb0_);
 }
 
 // ---- IGEMV ----------------------------------------------------------------------------------------------------------
@@ -413,6 +452,9 @@ __device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int l
   const View &v = C.v;
   WarpSmem &s   = C.s;
   const int nc  = v.meta[M_NKC];
+  CTA_PT(ti0_);
+  CTA_PCNT(9, 1);
+  CTA_PCNT(10, nnz);
   unsigned long long *bk = (unsigned long long *)(v.b + (size_t)kappa * v.ldb);
   for (int c0 = 32 * w; c0 < nc; c0 += 32 * CTA_WARPS)
   {
@@ -448,6 +490,7 @@ __device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int l
       bk[c] = acc;
   }
   cta_bar(2);
+  CTA_PADD(11, ti0_);
 }
 
 #if B200_MU_CACHE

@@ -59,11 +59,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 
 int b200gso_lll_warp_attrs(size_t smem_bytes)
 {
+  (void)smem_bytes;  // process-wide kernels: always the opt-in maximum (a smaller handle must not lower it)
   const void *fns[] = {(const void *)k_lll<4>,           (const void *)k_lll<8>,           (const void *)k_lll<16>,
                        (const void *)k_size_reduction<4>, (const void *)k_size_reduction<8>,
                        (const void *)k_size_reduction<16>};
   for (const void *f : fns)
-    CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN_MAX));
   return 0;
 }
 

@@ -81,9 +81,20 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 
 }  // namespace
 
+// profile builds: the cooperative operations' device-clock counters (gso_cta.cuh); zeros otherwise
+int b200gso_lll_cta_prof(long long *out32)
+{
+  memset(out32, 0, 32 * sizeof(long long));
+#ifdef B200_LLL_PROFILE
+  CK(cudaMemcpyFromSymbol(out32, g_cta_prof, 32 * sizeof(long long)));
+#endif
+  return 0;
+}
+
 int b200gso_lll_cta_attrs(int d, int n)
 {
-  const int sm = B200_MU_CACHE ? 227 * 1024 : (int)(cta_smem_doubles(d, n) * sizeof(double));
+  (void)d, (void)n;  // process-wide kernels: always the opt-in maximum (a smaller handle must not lower it)
+  const int sm = SMEM_OPTIN_MAX;
   CK(cudaFuncSetAttribute((const void *)k_lll_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute((const void *)k_lll_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute((const void *)k_lll_cta<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -98,9 +109,10 @@ int b200gso_lll_cta_launch(b200gso *h, int mode, double delta, double eta, int k
 #if B200_MU_CACHE
 #define LLL_CTA_EXTRA_ARG , mu_panels
     int mu_panels = 0;
-    if (getenv("B200_LLL_MU_SMEM") && atoi(getenv("B200_LLL_MU_SMEM")))
+    static const int mu_smem_on = getenv("B200_LLL_MU_SMEM") ? atoi(getenv("B200_LLL_MU_SMEM")) : 1;
+    if (mu_smem_on)
     {
-      // opt-in (not yet measured): cache as many leading mu panels as fit into the 227 KB of the CTA
+      // cache as many leading mu panels as fit into the 227 KB of the CTA
       while (mu_panels < n_panels(S.d) && sm + mu_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
         mu_panels++;
       sm += mu_panel_base(mu_panels) * sizeof(double);

@@ -428,144 +428,9 @@ template <int NPL> __global__ void hk_update_R(HBatch S, int i, int last_j)
   if (hsetup(S, v, sR, sP, lane))
     w_update_R<NPL>(v, i, last_j, sR, sP, lane);
 }
-// EXPERIMENTAL variant of update_R for batches (B200_HH_CTA32=1; written at the end of round 1, not yet run on
-// hardware).  ncu of hk_update_R shows 67 % issue-slot utilisation at 0.19 of the HBM peak: the kernel is bound by the ONE
-// lane per warp that adds the ordered chain.  Here a CTA of 32 warps serves 32 lattices; every warp still forms its own
-// lattice's products V_j[k] * R_i[k] (coalesced row loads, next row prefetched), but the 32 ordered sums of a reflection
-// are added by the 32 LANES of warp 0 at once (one lattice per lane, rows of the product buffer skewed by an odd stride),
-// so the serial adds run 32 wide.  Same products, same ascending chain, same axpy: bit-identical results.
-template <int NPL> __global__ void __launch_bounds__(1024, 1) hk_update_R_cta32(HBatch S, int i, int last_j)
-{
-  extern __shared__ __align__(16) double smem[];
-  const int n = S.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int npad = n | 1;  // odd row stride: lane l of the summing warp walks row l
-  double *sR = smem + (size_t)w * npad;                       // R_i of this warp's lattice
-  double *sP = smem + (size_t)32 * npad + (size_t)w * npad;   // products of this warp's lattice
-  double *sPall = smem + (size_t)32 * npad;
-  double *sS = smem + (size_t)64 * npad;                      // [32] sums
-  const int l = blockIdx.x * 32 + w;
-  const bool have = l < S.B;
-  HView v;
-  if (have)
-    v = hview(S, l);
-  const bool act = have && !v.meta[HM_UPDATED];
-  __shared__ int s_act[32];
-  if (lane == 0)
-    s_act[w] = act ? 1 : 0;
-  double *Rr = act ? v.R + (size_t)i * n : nullptr;
-  if (act)
-    for (int k = lane; k < n; k += 32)
-      sR[k] = Rr[k];
-  double *hrow = (act && v.keep_hist) ? v.hist + (size_t)v.hslot[i] * n * n : nullptr;
-  double vk[NPL], vn[NPL];
-#pragma unroll
-  for (int u = 0; u < NPL; u++)
-  {
-    const int k = 32 * u + lane;
-    vk[u]       = (act && i > 0 && k < n) ? v.V[k] : 0.0;
-    vn[u]       = 0.0;
-  }
-  __syncthreads();
-  for (int j = 0; j < i; j++)
-  {
-    const int kb = j & ~31;
-    if (act && j + 1 < i)
-    {
-      const double *Vn = v.V + (size_t)(j + 1) * n;
-      const int kbn    = (j + 1) & ~31;
-#pragma unroll
-      for (int u = 0; u < NPL; u++)
-      {
-        const int k = kbn + 32 * u + lane;
-        vn[u]       = (k >= j + 1 && k < n) ? Vn[k] : 0.0;
-      }
-    }
-    if (act)
-    {
-#pragma unroll
-      for (int u = 0; u < NPL; u++)
-      {
-        const int k = kb + 32 * u + lane;
-        if (k >= j && k < n)
-          sP[k] = __dmul_rn(vk[u], sR[k]);
-      }
-    }
-    __syncthreads();
-    if (w == 0 && s_act[lane])
-    {
-      const double *p = sPall + (size_t)lane * npad;
-      double r        = p[j];
-      for (int k = j + 1; k < n; k++)
-        r = __dadd_rn(r, p[k]);
-      sS[lane] = r;
-    }
-    __syncthreads();
-    if (act)
-    {
-      const double f0 = -sS[w];
-#pragma unroll
-      for (int u = 0; u < NPL; u++)
-      {
-        const int k = kb + 32 * u + lane;
-        if (k >= j && k < n)
-        {
-          double r = __dadd_rn(sR[k], __dmul_rn(vk[u], f0));
-          if (k == j)
-            r = __dmul_rn(v.sigma[j], r);
-          sR[k] = r;
-          if (hrow)
-            hrow[(size_t)j * n + k] = r;
-        }
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < NPL; u++)
-      vk[u] = vn[u];
-  }
-  if (act)
-  {
-    for (int k = lane; k < n; k += 32)
-      Rr[k] = sR[k];
-    __syncwarp();
-    if (last_j)
-      w_update_R_last(v, i, sP, lane);
-  }
-}
-
-static bool launch_update_R_cta32(const HBatch &S, cudaStream_t st, int i, int last_j)
-{
-  const size_t smem = ((size_t)64 * (S.n | 1) + 32) * sizeof(double);
-  if (smem > (size_t)227 * 1024)
-    return false;
-  const int need = (S.n + 31) / 32 + 1, grid = (S.B + 31) / 32;
-#define HH_CTA32(NPL_)                                                                                              \
-  do                                                                                                                \
-  {                                                                                                                 \
-    if (cudaFuncSetAttribute((const void *)hk_update_R_cta32<NPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                             (int)smem) != cudaSuccess)                                                              \
-    {                                                                                                               \
-      cudaGetLastError();                                                                                           \
-      return false;                                                                                                 \
-    }                                                                                                               \
-    hk_update_R_cta32<NPL_><<<grid, 1024, smem, st>>>(S, i, last_j);                                                \
-  } while (0)
-  if (need <= 4)
-    HH_CTA32(4);
-  else if (need <= 8)
-    HH_CTA32(8);
-  else if (need <= 14)
-    HH_CTA32(14);
-  else
-    return false;
-#undef HH_CTA32
-  return true;
-}
 
 static void launch_update_R(const HBatch &S, int grid, size_t smem, cudaStream_t st, int i, int last_j)
 {
-  if (getenv("B200_HH_CTA32") && atoi(getenv("B200_HH_CTA32")) && launch_update_R_cta32(S, st, i, last_j))
-    return;
   // a lane's slice of a row must fit NPL registers even when the row starts in the middle of a 32-column group
   const int need = (S.n + 31) / 32 + 1;
   if (need <= 4)
@@ -935,7 +800,7 @@ int b200hh_create(b200hh_t **out, int batch, int d, int n, int flags, int device
                        (const void *)hk_swap,        (const void *)hk_recover_R,   (const void *)hk_hlll<4>,
                        (const void *)hk_hlll<8>,     (const void *)hk_hlll<14>,     (const void *)hk_hlll<32>};
   for (const void *f : fns)
-    CKH(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKH(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // process-wide: opt-in maximum, never lowered
   CKH(cudaMemsetAsync(S.b, 0, (size_t)batch * d * S.ldb * 8, h->stream));
   CKH(cudaMemsetAsync(S.bf, 0, batch * dn * 8, h->stream));
   CKH(cudaMemsetAsync(S.R, 0, batch * dn * 8, h->stream));

@@ -33,8 +33,33 @@ def merge_enum_results(local, d, group=None, device=None):
     return dict(solutions=sols, nodes=nodes.cpu().numpy().astype(np.uint64), leaves=int(leaves.item()))
 
 
+_attached = {}
+
+
+def attach_peers(group=None, device_index=0):
+    """Once per job: let the ranks' enumerators reach each other's radius word and rank 0's subtree ticket over NVLink
+    (CUDA IPC; include/b200enum.h b200enum_ipc_*).  The 64-byte handles are all-gathered through the process group
+    (NCCL on GPUs).  Without it sharded calls fall back to a static deal of the roots with private radii."""
+    from . import enumeration as en
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    key = (id(group), device_index)
+    if world < 2 or _attached.get(key):
+        return bool(_attached.get(key))
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", device_index) if nccl else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(en.ipc_export(device_index)), dtype=torch.uint8).to(dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    en.ipc_attach(device_index, world, rank, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    dist.barrier(group=group)
+    _attached[key] = True
+    return True
+
+
 def enumerate_svp_distributed(mut, rdiag, pruning, maxdist, group=None, device_index=0, fixed_radius=False):
-    """sharded enumeration across the ranks of `group` (one GPU per rank)."""
+    """sharded enumeration across the ranks of `group` (one GPU per rank).  After attach_peers() the ranks claim subtree
+    roots from one shared ticket and push radius improvements to each other inside the kernel (NVLink peer memory);
+    the result merge below (NCCL) is also what keeps call k+1 from starting before every rank finished call k."""
     from . import enumeration as en
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = en.enumerate_svp(mut, rdiag, pruning, maxdist, fixed_radius=fixed_radius, devices=[device_index],

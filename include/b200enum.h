@@ -8,10 +8,10 @@
  * plain pointers, and INTEGRATION.md shows the 30-line C++ adapter with the typedef'd signature that a maintainer
  * registers through set_external_enumerator (fplll_b200/csrc/fplll_extenum_adapter.cpp).
  *
- * Scope: SVP, primal, no sub-solutions — what BKZ's svp_reduction asks for
- * (bkz.cpp:329-331 with FastEvaluator(1) — bkz.h:324).  dual / findsubsols requests are answered with
- * B200ENUM_UNSUPPORTED so the adapter returns nodes[0] = ~0 and fplll falls back (enumerate_ext.cpp:88), exactly
- * like the bundled enumlib does for dual (enum-parallel/enumlib.cpp:98-104).
+ * Scope: SVP enumeration, primal (what BKZ's svp_reduction asks for, bkz.cpp:329-331 with
+ * FastEvaluator(1) — bkz.h:324) and dual (SD-BKZ / slide reduction, bkz.cpp:443-520), with or without sub-solutions:
+ * the plugin never has to decline a request of the hook (the bundled enumlib declines dual,
+ * enum-parallel/enumlib.cpp:98-104).
  */
 #ifndef B200ENUM_H
 #define B200ENUM_H
@@ -31,12 +31,19 @@ extern "C" {
 
 /* flags */
 #define B200ENUM_FIXED_RADIUS 1 /* never shrink the radius: counts every leaf inside it (known-answer tests) */
-#define B200ENUM_DUAL 2         /* request flags of the hook; both are declined */
-#define B200ENUM_FINDSUBSOLS 4
+#define B200ENUM_DUAL 2         /* dual SVP enumeration (enumerate.cpp:100-124): mut/rdiag are the PRIMAL block's; the
+                                 * enumerator forms the reversed dual basis itself and returns coefficients in the
+                                 * block's own order */
+#define B200ENUM_FINDSUBSOLS 4  /* report the best partial vector per level (enumerate_base.cpp:36-40): b200enum_run_ex */
+#define B200ENUM_IPC_HANDLE_BYTES 64
 
 /* extenum_cb_process_sol (enumerate_ext_api.h:62-63): gets the squared length and the coefficient vector of a new
  * solution, returns the new enumeration bound. */
 typedef double (*b200enum_sol_cb)(void *ctx, double dist, const double *sol);
+
+/* extenum_cb_process_subsol (enumerate_ext_api.h:70-71): squared length of the partial vector, its coefficients
+ * (zero below `offset`) and the level it starts at. */
+typedef void (*b200enum_subsol_cb)(void *ctx, double dist, const double *subsol, int offset);
 
 typedef struct
 {
@@ -70,6 +77,22 @@ typedef struct
 int b200enum_run(int dim, double maxdist, const double *mut, const double *rdiag, const double *pruning, int flags,
                  const int *devices, int ndev, int shard_rank, int shard_world, b200enum_sol_cb cb, void *ctx,
                  uint64_t *nodes, b200enum_stats *stats);
+
+/* Same, plus the sub-solution callback (required with B200ENUM_FINDSUBSOLS): called once per level that has a partial
+ * vector shorter than rdiag[level], with the shortest one found (what Evaluator::eval_sub_sol keeps, evaluator.h:191-205). */
+int b200enum_run_ex(int dim, double maxdist, const double *mut, const double *rdiag, const double *pruning, int flags,
+                    const int *devices, int ndev, int shard_rank, int shard_world, b200enum_sol_cb cb,
+                    b200enum_subsol_cb subcb, void *ctx, uint64_t *nodes, b200enum_stats *stats);
+
+/* One process per GPU (torch.distributed): let the ranks' enumerators reach each other's radius word and rank 0's
+ * subtree ticket over NVLink (CUDA IPC).  Every rank exports a handle for its device, the job all-gathers the
+ * world*64 bytes (NCCL / gloo), every rank attaches.  After that, sharded calls (shard_world == world) claim subtree
+ * roots from ONE ticket and push every radius improvement to all peers — enumlib's shared counter and shared radius
+ * (enum-parallel/enumeration.h:62-81,460-475) — instead of a static deal with private radii.  Ranks must not start
+ * call k+1 before every rank has finished call k (the result exchange after each call guarantees that). */
+int b200enum_ipc_export(int device, unsigned char *handle64);
+int b200enum_ipc_attach(int device, int world, int rank, const unsigned char *handles);
+int b200enum_ipc_detach(int device);
 
 const char *b200enum_last_error(void);
 int b200enum_device_count(void);

@@ -147,6 +147,13 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
  * batches that are a multiple of it run in full waves.  Negative on error. */
 int b200gso_resident_lattices(b200gso_t *h);
 
+/* Profiling builds only (-DB200_LLL_PROFILE): device-clock phase counters of the last LLL call of this process
+ * (update_gso_row, Babai rest, Lovasz, move_row+set_r, gather/scan, back-substitution, integer rows, row_op_end).
+ * All zero in release builds.  `stats` of b200gso_lll is always batch*4 longs. */
+int b200gso_lll_profile(long *out8);
+/* ... and the counters of the CTA-cooperative operations, accumulated over the process (slots: csrc/gso_cta.cuh). */
+int b200gso_lll_cta_profile(long long *out32);
+
 /* Synchronise the handle's stream (all calls above are stream-ordered on one stream per handle). */
 int b200gso_sync(b200gso_t *h);
 

@@ -256,6 +256,30 @@ def enum_svp(mut, rdiag, pruning, maxdist, shrink=True):
     return dict(nsols=int(n), best=best.value, sol=sol, nodes=nodes)
 
 
+def enum_svp_ex(mut, rdiag, pruning, maxdist, shrink=True, dual=False, findsubsols=False):
+    """oracle/enum_oracle.c::oenum_svp_ex: dual enumeration and sub-solutions.  mut / rdiag: the primal block's."""
+    L = lib()
+    d = len(rdiag)
+    mut = np.ascontiguousarray(mut, np.float64).reshape(d, d)
+    rdiag = np.ascontiguousarray(rdiag, np.float64)
+    pr = None if pruning is None else np.ascontiguousarray(pruning, np.float64)
+    sol = np.zeros(d)
+    best = C.c_double()
+    nodes = np.zeros(d, np.uint64)
+    subdist = np.full(d, -1.0)
+    subsol = np.zeros((d, d))
+    P = C.POINTER
+    L.oenum_svp_ex.restype = C.c_long
+    L.oenum_svp_ex.argtypes = [C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), C.c_double, C.c_int, C.c_int,
+                               C.c_int, P(C.c_double), P(C.c_double), P(C.c_uint64), P(C.c_double), P(C.c_double)]
+    n = L.oenum_svp_ex(d, mut.ctypes.data_as(P(C.c_double)), rdiag.ctypes.data_as(P(C.c_double)),
+                       pr.ctypes.data_as(P(C.c_double)) if pr is not None else None, float(maxdist),
+                       1 if shrink else 0, 1 if dual else 0, 1 if findsubsols else 0,
+                       sol.ctypes.data_as(P(C.c_double)), C.byref(best), nodes.ctypes.data_as(P(C.c_uint64)),
+                       subdist.ctypes.data_as(P(C.c_double)), subsol.ctypes.data_as(P(C.c_double)))
+    return dict(nsols=int(n), best=best.value, sol=sol, nodes=nodes, subdist=subdist, subsol=subsol)
+
+
 def read_enum_records(path):
     """Parse the records ref_probe's `enum` appends (layout in oracle/ref_probe.cpp)."""
     raw = open(path, "rb").read()
@@ -264,7 +288,8 @@ def read_enum_records(path):
         hdr = np.frombuffer(raw, np.int32, 4, off)
         off += 16
         assert hdr[0] == 0x454E554D
-        d, found, mode = int(hdr[1]), int(hdr[2]), int(hdr[3])
+        d, found, mode = int(hdr[1]), int(hdr[2]), int(hdr[3]) & 15
+        dual, subsols = bool(int(hdr[3]) & 16), bool(int(hdr[3]) & 32)
         md, best = np.frombuffer(raw, np.float64, 2, off)
         off += 16
         normexp = int(np.frombuffer(raw, np.int64, 1, off)[0])
@@ -274,7 +299,7 @@ def read_enum_records(path):
         nodes = np.frombuffer(raw, np.uint64, d, off).copy()
         off += 8 * d
         rec = dict(d=d, found=found, mode=mode, maxdist=float(md), best=float(best), normexp=normexp, sol=sol,
-                   nodes=nodes)
+                   nodes=nodes, dual=dual, subsols=subsols)
         if mode == 2:
             rec["mut"] = np.frombuffer(raw, np.float64, d * d, off).reshape(d, d).copy()
             off += 8 * d * d
@@ -282,6 +307,11 @@ def read_enum_records(path):
             off += 8 * d
             rec["pruning"] = np.frombuffer(raw, np.float64, d, off).copy()
             off += 8 * d
+        if subsols:
+            rec["subdist"] = np.frombuffer(raw, np.float64, d, off).copy()
+            off += 8 * d
+            rec["subsol"] = np.frombuffer(raw, np.float64, d * d, off).reshape(d, d).copy()
+            off += 8 * d * d
         out.append(rec)
     return out
 

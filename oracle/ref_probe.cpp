@@ -207,6 +207,9 @@ static void time_update_gso_mt(int reps, int threads, int per)
  *   PRUNEFILE ("-" = none).  MODE = internal (EnumerationDyn, enumerate.cpp:58) | enumlib (the bundled parallel
  *   enumerator through the extenum hook) | capture (a hook that records exactly what the plugin API hands an
  *   external enumerator — enumerate_ext.cpp:48-148 — and declines, so the internal enumerator then runs).
+ *   A suffix of the mode adds the other two cases of the hook: internal_dual (dual SVP of the block as svp_reduction
+ *   asks for it, bkz.cpp:277-318: max_dist = FACTOR / r(LAST-1,LAST-1)), internal_subsols, internal_dual_subsols
+ *   (evaluator with find_subsolutions; the record then ends with f64 subdist[d] (-1 = none), f64 subsol[d*d]).
  * OUT (binary, appended): int32 magic 0x454e554d, d, found, mode; f64 maxdist_norm (capture mode: as handed to the
  *   hook, else -1), f64 best_dist (evaluator's, denormalised), int64 normexp; f64 sol[d]; u64 nodes[d];
  *   capture mode only: f64 mut[d*d] (transposed layout of enumerate_ext.cpp:108-121), f64 rdiag[d], f64 pruning[d]
@@ -253,7 +256,8 @@ static void run_enum(GsoL &m, int first, int last, double factor, const string &
     }
   }
   int imode = 0;
-  if (mode == "internal")
+  const bool dual = mode.find("dual") != string::npos, subsols = mode.find("subsols") != string::npos;
+  if (mode.rfind("internal", 0) == 0)
     set_external_enumerator(nullptr);
   else if (mode == "enumlib")
   {
@@ -266,20 +270,47 @@ static void run_enum(GsoL &m, int first, int last, double factor, const string &
     imode   = 2;
     g_cap   = EnumCapture();
   }
-  FastEvaluator<FP_NR<double>> ev;
+  FastEvaluator<FP_NR<double>> ev(1, EVALSTRATEGY_BEST_N_SOLUTIONS, subsols);
   Enumeration<Z_NR<long>, FP_NR<double>> en(m, ev);
   long expo;
-  FP_NR<double> maxd = m.get_r_exp(first, first, expo);
+  FP_NR<double> maxd = m.get_r_exp(dual ? last - 1 : first, dual ? last - 1 : first, expo);
+  if (dual)
+  {
+    maxd.pow_si(maxd, -1, GMP_RNDU);  // bkz.cpp:312-316
+    expo *= -1;
+  }
   maxd.mul(maxd, factor);
   double t0 = now();
-  en.enumerate(first, last, maxd, expo, vector<FP_NR<double>>(), vector<enumxt>(), pr, false);
+  en.enumerate(first, last, maxd, expo, vector<FP_NR<double>>(), vector<enumxt>(), pr, dual);
   double sec = now() - t0;
   set_external_enumerator(bundled);
   FILE *f        = fopen(out.c_str(), "ab");
   int found      = ev.empty() ? 0 : 1;
-  int32_t hdr[4] = {0x454e554d, d, found, imode};
+  int32_t hdr[4] = {0x454e554d, d, found, imode | (dual ? 16 : 0) | (subsols ? 32 : 0)};
   wr(f, hdr, 4);
   double md = imode == 2 ? g_cap.maxdist : -1.0;
+  if (dual)
+  {
+    // The hook's own normalisation of a DUAL radius (enumerate_ext.cpp:72: mul_2si(fmaxdist, _normexp - fmaxdistexpo))
+    // differs from EnumerationDyn's (enumerate.cpp:92-98: normexp negated, fmaxdistexpo - normexp) by 2^(2 * expo of
+    // r(last-1)) whenever GSO_ROW_EXPO is on, so what the capture hook saw is not the radius the reference's own dual
+    // enumeration (whose nodes / solution this record holds) ran with.  Record the latter, restated:
+    long rexpo, normexp = -1;
+    for (int i = 0; i < d; ++i)
+    {
+      FP_NR<double> fr = m.get_r_exp(i + first, i + first, rexpo);
+      normexp          = std::max(normexp, rexpo + fr.exponent());
+    }
+    normexp *= -1;
+    long e2;
+    FP_NR<double> md2 = m.get_r_exp(last - 1, last - 1, e2);
+    md2.pow_si(md2, -1, GMP_RNDU);
+    e2 *= -1;
+    md2.mul(md2, factor);
+    FP_NR<double> nrm;
+    nrm.mul_2si(md2, e2 - normexp);
+    md = nrm.get_d(GMP_RNDU);
+  }
   wr(f, &md, 1);
   double best = found ? ev.begin()->first.get_d() : -1.0;
   wr(f, &best, 1);
@@ -303,6 +334,19 @@ static void run_enum(GsoL &m, int first, int last, double factor, const string &
     wr(f, g_cap.mut.data(), g_cap.mut.size());
     wr(f, g_cap.rdiag.data(), d);
     wr(f, g_cap.pruning.data(), d);
+  }
+  if (subsols)
+  {
+    vector<double> sd(d, -1.0), ss((size_t)d * d, 0.0);
+    for (size_t k = 0; k < ev.sub_solutions.size() && (int)k < d; k++)
+      if (!ev.sub_solutions[k].second.empty())
+      {
+        sd[k] = ev.sub_solutions[k].first.get_d();
+        for (int i = 0; i < d; i++)
+          ss[k * d + i] = ev.sub_solutions[k].second[i].get_d();
+      }
+    wr(f, sd.data(), d);
+    wr(f, ss.data(), ss.size());
   }
   fclose(f);
   printf("enum d=%d mode=%s found=%d best=%.17g nodes=%llu sec=%.6f\n", d, mode.c_str(), found, best,

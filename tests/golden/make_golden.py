@@ -181,5 +181,38 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def enum_dual_subsol_fixtures():
+    """Dual SVP enumeration and sub-solutions: block [140,170) of the LLL-reduced r200 basis, unpruned,
+    through the capture hook (records what the plugin API hands an external enumerator, then the reference's own
+    enumerator runs).  Standalone: python tests/golden/make_golden.py --dual"""
+    g = np.load(os.path.join(HERE, "r200_lll_update_gso.npz"))
+    os.makedirs(TMP, exist_ok=True)
+    mat = os.path.join(TMP, "r200_red.txt")
+    O.write_matrix(mat, g["b"])
+    out = os.path.join(TMP, "enum_dual_fixture.bin")
+    if os.path.exists(out):
+        os.remove(out)
+    modes = ["capture", "capture_dual", "capture_subsols", "capture_dual_subsols"]
+    script = "load %s\ntolong\ngso l 2\nupdate_gso\n" % mat + "".join(
+        "enum 140 170 0.99 - %s %s\n" % (out, m) for m in modes)
+    print(O.run_ref(script, timeout=600))
+    recs = O.read_enum_records(out)
+    arrs = dict(mut=recs[0]["mut"], rdiag=recs[0]["rdiag"], pruning=recs[0]["pruning"])
+    for m, r in zip(["primal", "dual", "subsols", "dual_subsols"], recs):
+        assert np.array_equal(r["mut"], recs[0]["mut"]) and np.array_equal(r["rdiag"], recs[0]["rdiag"])
+        arrs[m + "_maxdist"] = np.float64(r["maxdist"])
+        arrs[m + "_best"] = np.float64(r["best"])
+        arrs[m + "_normexp"] = np.int64(r["normexp"])
+        arrs[m + "_sol"] = r["sol"]
+        arrs[m + "_nodes"] = r["nodes"]
+        if r["subsols"]:
+            arrs[m + "_subdist"] = r["subdist"]
+            arrs[m + "_subsol"] = r["subsol"]
+    np.savez_compressed(os.path.join(HERE, "enum_r200_b30_dual_subsols.npz"), **arrs)
+
+
 if __name__ == "__main__":
-    main()
+    if "--dual" in sys.argv:
+        enum_dual_subsol_fixtures()
+    else:
+        main()

@@ -111,23 +111,54 @@ def test_reference_bkz_with_the_plugin_installed(tmp_path):
 def test_two_devices_in_one_process_visit_the_same_nodes(en):
     """b200enum_run(devices = [0, 1]): subtree roots dealt over two GPUs of the box from ONE process (what the BKZ driver
     does with `devices`); fixed radius, so the per-level node counts must equal the oracle's.  Needs two GPUs."""
-    import os
     from fplll_b200._lib import load
-    if not os.environ.get("B200_TEST_MULTI_GPU"):
-        pytest.skip("set B200_TEST_MULTI_GPU=1 on a box with two GPUs (gpurun --gpus 2)")
     if load("libb200enum.so").b200enum_device_count() < 2:
-        pytest.skip("one GPU visible")
+        pytest.skip("one GPU visible (the driver's round-end run has one; gpurun --gpus 2 runs this)")
+    # a call this small stays on the first device (hand-off threshold B200_ENUM_FAN_NODES, 4 M nodes) ...
     z = H.gold("enum_r200_b30_unpruned.npz")
     R = 0.55 * float(z["maxdist"])
     ref = O.enum_svp(z["mut"], z["rdiag"], None, R, shrink=False)
-    for _ in range(2):  # second call: both device contexts already exist
+    for _ in range(2):
         res = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True, devices=[0, 1])
-        assert res["stats"]["n_devices"] == 2
+        assert res["stats"]["n_devices"] == 1
         assert np.array_equal(res["nodes"], ref["nodes"])
+    # ... the 5.6e8-node BKZ-60 block is handed off: both devices claim subtrees from one ticket over NVLink and the
+    # fleet still visits exactly the reference's nodes
+    z = H.gold("enum_r200_b60_pruned_140.npz")
+    for _ in range(2):  # second call: both device contexts already exist
+        res = en.enumerate_svp(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), devices=[0, 1])
+        assert res["stats"]["n_devices"] == 2
+        assert np.array_equal(res["nodes"], z["nodes"])
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_EXPERIMENTAL"),
-                    reason="added after the round's GPU budget was spent: set B200_TEST_EXPERIMENTAL=1")
+def test_dual_enumeration_and_subsolutions_equal_reference(en):
+    """the hook's dual / findsubsols requests are served on the device.  Fixed radius: per-level node
+    counts equal the oracle's (pinned to the reference in tests/test_enum_oracle.py); shrinking radius: the best vector
+    and the per-level sub-solutions are the reference's own (tests/golden/enum_r200_b30_dual_subsols.npz)."""
+    z = H.gold("enum_r200_b30_dual_subsols.npz")
+    for name, dual, subs in (("dual", True, False), ("subsols", False, True), ("dual_subsols", True, True)):
+        R = float(z[name + "_maxdist"])
+        ne = int(z[name + "_normexp"])
+        ref = O.enum_svp_ex(z["mut"], z["rdiag"], None, 0.7 * R, shrink=False, dual=dual, findsubsols=subs)
+        res = en.enumerate_svp(z["mut"], z["rdiag"], None, 0.7 * R, fixed_radius=True, dual=dual, findsubsols=subs)
+        assert np.array_equal(res["nodes"], ref["nodes"]), name
+        res = en.enumerate_svp(z["mut"], z["rdiag"], None, R, dual=dual, findsubsols=subs)
+        dist, x = res["solutions"][-1]
+        assert dist * 2.0 ** ne == float(z[name + "_best"]), name
+        assert np.array_equal(x, z[name + "_sol"]) or np.array_equal(x, -z[name + "_sol"]), name
+        if subs:
+            # a shrinking radius changes which nodes exist below a solution, not which partial vectors are shortest
+            # above the level where the radius first moved; the full-radius walk (fixed) must reproduce every level
+            full = en.enumerate_svp(z["mut"], z["rdiag"], None, R, fixed_radius=True, dual=dual, findsubsols=True)
+            oref = O.enum_svp_ex(z["mut"], z["rdiag"], None, R, shrink=False, dual=dual, findsubsols=True)
+            for k in range(len(z["rdiag"])):
+                if oref["subdist"][k] > 0:
+                    assert k in full["subsolutions"], (name, k)
+                    assert full["subsolutions"][k][0] == oref["subdist"][k], (name, k)
+                else:
+                    assert k not in full["subsolutions"], (name, k)
+
+
 def test_reference_svp_known_answer_on_device(en):
     """tests/test_svp.cpp:373-374 end to end on the device: device LLL, device enumeration with radius |b_0|^2, squared
     norm of the result equals that of lattices/example_svp_out."""

@@ -53,3 +53,20 @@ def test_reference_svp_known_answer():
         v = np.rint(res["sol"]).astype(np.int64) @ b
         best = min(best, int((v.astype(object) ** 2).sum()))
     assert best == want
+
+
+def test_oracle_dual_and_subsolutions_match_reference():
+    """the dual SVP walk (chains over alpha, reversed inverted basis, enumerate.cpp:100-124) and the
+    per-level sub-solutions (enumerate_base.cpp:36-40) of the reference's own enumerator on block [140,170) of the
+    LLL-reduced r200 basis (tests/golden/enum_r200_b30_dual_subsols.npz, made by make_golden.py --dual)."""
+    z = H.gold("enum_r200_b30_dual_subsols.npz")
+    for name, dual, subs in (("primal", False, False), ("dual", True, False), ("subsols", False, True),
+                             ("dual_subsols", True, True)):
+        res = O.enum_svp_ex(z["mut"], z["rdiag"], None, float(z[name + "_maxdist"]), dual=dual, findsubsols=subs)
+        ne = int(z[name + "_normexp"])
+        assert np.array_equal(res["nodes"], z[name + "_nodes"]), name
+        assert res["best"] * 2.0 ** ne == float(z[name + "_best"]), name
+        assert np.array_equal(res["sol"], z[name + "_sol"]), name
+        if subs:
+            assert np.array_equal(np.where(res["subdist"] > 0, res["subdist"] * 2.0 ** ne, -1.0), z[name + "_subdist"])
+            assert np.array_equal(res["subsol"], z[name + "_subsol"])

@@ -239,11 +239,8 @@ def test_ranged_lll_and_size_reduction_resume_are_exact(fb, lll_mode):
     assert np.array_equal(md.b[0], bb)
 
 
-_experimental = pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_EXPERIMENTAL"),
-                                   reason="experimental entry points (not yet run on hardware): set B200_TEST_EXPERIMENTAL=1")
 
 
-@_experimental
 @pytest.mark.parametrize("mode", [0, 1])
 def test_blocked_update_gso_small_entries_bit_exact(fb, mode):
     """b200gso_update_gso_blocked: Gram matrix in 32x32 tiles, then the row sweeps.  Entries below 2^20 make every
@@ -260,7 +257,6 @@ def test_blocked_update_gso_small_entries_bit_exact(fb, mode):
         H.assert_state_equal(H.lattice_state(st, l), mo.state(), "blocked mode %d lattice %d" % (mode, l))
 
 
-@_experimental
 def test_blocked_update_gso_large_entries(fb):
     """40-bit entries: the ordered mode stays bit-exact, the DMMA mode is within north_star's 1e-9 on mu and r."""
     rng = np.random.default_rng(52)

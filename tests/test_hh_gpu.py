@@ -124,13 +124,3 @@ def test_device_hlll_needs_history():
     m = MatHouseholder(H.gold("hlll_long.npz")["u40_in"], 5, keep_history=False)
     with pytest.raises(B200Error):
         m.hlll()
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_EXPERIMENTAL"),
-                    reason="experimental kernel (not yet run on hardware): set B200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("seed,d,n,bits,batch", [(21, 24, 30, 12, 3), (22, 40, 40, 30, 35), (23, 70, 75, 10, 2)])
-def test_update_R_cta32_variant_bit_exact(seed, d, n, bits, batch, monkeypatch):
-    """B200_HH_CTA32=1: update_R with 32 lattices per CTA and the ordered sums added one lattice per lane — the same
-    HLLL-like call sequence must give the oracle's R, V, sigma bit for bit (batch 35 = two CTAs, one partly filled)."""
-    monkeypatch.setenv("B200_HH_CTA32", "1")
-    test_hlll_like_sequence_bit_exact(seed, d, n, bits, batch)
