@@ -119,7 +119,8 @@ struct EnumArgs
   unsigned long long *A_peer[MAX_PEERS];  // the other devices' radius words
   int n_peer;
   unsigned long long node_cap; // suspend at a round boundary once this many nodes are visited (0 = never)
-  unsigned yield_nodes;          // a walker re-checks the split / yield conditions every this many nodes
+  unsigned yield_nodes;          // a walker re-checks the split / yield conditions every this many nodes ...
+  unsigned yield_small;          // ... or this many, in a round with fewer tasks than warps
   unsigned budget0, budget_mul;  // nodes a walker may visit before it must split: budget0 * mul^round (capped)
   unsigned long long *nodes;   // [d]
   SolRec *sols_fast, *sols_more;
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
   int top      = 0;   // highest level this walker still owns
   unsigned n   = 0;   // nodes since the last split
   unsigned nr  = 0;   // nodes of this round
-  unsigned next_check = a.yield_nodes;
+  const unsigned ynodes = (my_share < total_warps) ? a.yield_small : a.yield_nodes;
+  unsigned next_check = ynodes;
   for (;;)
   {
     if (k == -2)
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
       cen[k] = h.cen;
       setx(k, h.xs);
       n      = 0;
-      next_check = a.yield_nodes;
+      next_check = ynodes;
     }
 
     // ---- one step of enumerate_loop (enumerate_base.cpp:193-254) ----
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
       //    ancestor's remaining siblings plus its current position become tasks of the next round — so the tail of
       //    a round is bounded by ~64 nodes instead of by the largest subtree.
       const bool dry = shared_round ? (*(volatile unsigned *)flags != 0u) : (*(volatile unsigned *)ticket >= end);
-      next_check     = n + a.yield_nodes;
+      next_check     = n + ynodes;
       if (dry || n >= budget)
       {
         int jj = top, given = 0;
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
           }
         }
         n          = 0;
-        next_check = a.yield_nodes;
+        next_check = ynodes;
       }
     }
     if (((++steps) & 63) == 0 && !a.fixed_radius)
@@ -699,6 +701,8 @@ struct Tuning
   unsigned budget0, budget_mul, yield_nodes;
   int bpsm, use_xs, xs_threads_cap;
   unsigned long long fan_nodes;
+  int min_roots;
+  unsigned yield_small;
   const char *trace;
 };
 const Tuning &tuning()
@@ -715,6 +719,9 @@ const Tuning &tuning()
     // hand-off threshold: a call that has visited this many nodes on the first device and still has work pending is
     // spread over all devices (4 M nodes = ~0.5 ms of one B200; the hand-off itself costs ~0.1 ms)
     q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 4000000);
+    q.min_roots   = (int)geti("B200_ENUM_MIN_ROOTS", MIN_ROOTS);
+    // rounds with fewer tasks than warps are bound by the latency of a lone walker (~0.35 us per node): yield sooner
+    q.yield_small = (unsigned)geti("B200_ENUM_YIELD_SMALL", 64);
     q.trace     = getenv("B200_ENUM_TRACE");  // append one line per call to this file
     return q;
   }();
@@ -818,7 +825,7 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
 
   // ---- host breadth phase ----
   Breadth br;
-  const size_t want = (size_t)MIN_ROOTS * (size_t)shard_world;
+  const size_t want = (size_t)tn.min_roots * (size_t)shard_world;
   breadth_phase(d, mut, rdiag, prun.data(), maxdist, dual, std::min<size_t>(want, MAX_ROOTS), MAX_ROOTS, br);
   const int T = (int)br.lev.size(), L = d - T;
   const std::vector<BNode> &leaf = br.lev[T - 1];
@@ -919,6 +926,7 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
     a.sub_bits = (unsigned long long *)(c->d_blk + DevCtx::OFF_SUBB);
     a.sols_fast = (SolRec *)c->d_blk, a.sols_more = c->d_sols_more, a.subs = c->d_subs;
     a.budget0 = tn.budget0, a.budget_mul = tn.budget_mul, a.yield_nodes = tn.yield_nodes;
+    a.yield_small = tn.yield_small;
     a.fixed_radius = fixed ? 1 : 0, a.dual = dual ? 1 : 0, a.findsubsols = subs ? 1 : 0;
     a.share_div = 1;
   };

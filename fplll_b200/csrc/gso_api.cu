@@ -851,8 +851,8 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
   int *d_st     = (int *)(h->d_stats + 4 * (size_t)S.B + 8);
   // few lattices (BKZ works on one): a whole CTA per lattice (k_lll_cta); many: one warp per lattice, the batch hides
   // the latencies.  B200_LLL_CTA=0 forces the one-warp kernels, B200_LLL_CTA_MAX moves the switch-over.
-  static const int cta_on  = getenv("B200_LLL_CTA") ? atoi(getenv("B200_LLL_CTA")) : 1;
-  static const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
+  const int cta_on  = getenv("B200_LLL_CTA") ? atoi(getenv("B200_LLL_CTA")) : 1;  // read per call: tests switch kernels
+  const int cta_max = getenv("B200_LLL_CTA_MAX") ? atoi(getenv("B200_LLL_CTA_MAX")) : 296;
   const bool cta = cta_on && S.B <= cta_max && S.d > 32;
   if (cta)
   {

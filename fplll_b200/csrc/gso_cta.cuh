@@ -180,7 +180,7 @@ __device__ inline double lane_dot_deep(const double *__restrict__ col, const dou
 // update_gso_row(i, last_j) for a row that is already discovered and has valid[i] <= last_j (the master checks both).
 // Same arithmetic as warp_update_gso_row: lane l of panel p owns column j = 32p + l,
 //   acc_j = g(i,j); acc_j -= mu(j,k) r(i,k) for k = 0 .. j-1 ascending.
-__device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int lane)
+B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int lane)
 {
   const View &v = C.v;
   WarpSmem &s   = C.s;
@@ -356,7 +356,7 @@ __device__ inline bool cta_update_gso_row(CoopShared &C, int i, int last_j, int 
 // ---- BACKSUB --------------------------------------------------------------------------------------------------------
 // X_j = rnd_we(babai_mu[j]); babai_mu[k] -= X_j * mu(j,k) for k < j, j descending (lll.cpp:202-214).  C.bm holds
 // babai_mu (columns < sr_end); the X_j land in s.xs[j], the per-panel masks of the non-zero ones in xmask[].
-__device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, int w, int lane)
+B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, int w, int lane)
 {
   const View &v = C.v;
   WarpSmem &s   = C.s;
@@ -447,7 +447,7 @@ __device__ inline void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_
 // b_kappa += sum_t lx_t * 2^e_t * b_{row_t} over the nnz compacted rows (lx in s.aux[t], (e << 32 | row) in s.murow[t]):
 // row_addmul_we (gso.cpp:236-262) fused over j; int64 arithmetic wraps, so the order of the additions is immaterial.
 // Warp w takes the column groups w, w + CTA_WARPS, ... of 32 columns.
-__device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int lane)
+B200_OPFN void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int lane)
 {
   const View &v = C.v;
   WarpSmem &s   = C.s;
@@ -496,7 +496,7 @@ __device__ inline void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int l
 #if B200_MU_CACHE
 // ---- MULOAD --------------------------------------------------------------------------------------------------------
 // (re)fill the shared-memory copies of the mu panels pa..pb (those that are cached) from global memory
-__device__ inline void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
+B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
 {
   const int tid = threadIdx.x;
   const int hi  = min(pb, C.mu_s_panels - 1);
@@ -530,7 +530,7 @@ __device__ inline void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lan
 // move_row(old_r, new_r) (gso.cpp:289-366) by the whole CTA: warp_move_row (gso_warp.cuh) with its lane-strided passes
 // (one column of mu / r / b / bf per lane, one Gram row per lane) strided over all CTA_WARPS * 32 threads instead; the
 // data movement per element is the same, only who carries it differs.
-__device__ inline void cta_move_row(CoopShared &C, int old_r, int new_r, int w, int lane)
+B200_OPFN void cta_move_row(CoopShared &C, int old_r, int new_r, int w, int lane)
 {
   const View &v = C.v;
   const int tid = threadIdx.x, NT = CTA_WARPS * 32;

@@ -54,7 +54,7 @@ struct LLLStats
 // LLLReduction::babai(kappa, size_reduction_end, size_reduction_start), lll.cpp:166-224.
 // MAXQ*32 >= d.  Returns RED_SUCCESS or the failing status (warp-uniform).
 template <int MAXQ, bool COOP = false>
-__device__ inline int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int sr_start, double eta,
+B200_OPFN int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int sr_start, double eta,
                                  int lane, long &iters, LLLStats *pst = nullptr, CoopShared *C = nullptr)
 {
   long max_expo = LONG_MAX;
@@ -309,7 +309,7 @@ __device__ inline bool warp_b_row_is_zero(const View &v, int i, int lane)
 }
 
 // get_gram(kappa,kappa) (gso.h:314-331) for the Lovasz test; computes the dot product if the entry is invalid.
-__device__ inline double warp_get_gram_diag(const View &v, WarpSmem &s, int i, int lane)
+B200_OPFN double warp_get_gram_diag(const View &v, WarpSmem &s, int i, int lane)
 {
   double *g  = v.gf + tri_off(i) + i;
   double val = *g;

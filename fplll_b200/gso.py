@@ -136,6 +136,29 @@ class MatGSO:
         f = np.ascontiguousarray(np.broadcast_to(np.asarray(f, np.float64), (self.batch,)))
         _ck(_lib().b200gso_set_r(self._h, i, j, _ptr(f, C.c_double)), "set_r")
 
+    def negate_row_of_b(self, i):
+        """MatGSO::negate_row_of_b (gso.h:291-297): integer row only; the caller brackets it with row_op_begin/end."""
+        _ck(_lib().b200gso_negate_row_of_b(self._h, i), "negate_row_of_b")
+
+    def get_block(self, first, beta, lattice=0):
+        """What Enumeration::enumerate pulls out of the GSO for block [first, first+beta) (enumerate_ext.cpp:91-148):
+        mut[k, j] = get_mu(first+j, first+k) for j > k (row_expo applied) and get_r_exp(first+i, first+i) as
+        (mantissa[beta], exponent[beta])."""
+        mut = np.empty((beta, beta))
+        rm = np.empty(beta)
+        re = np.empty(beta, np.int64)
+        _ck(_lib().b200gso_get_block(self._h, lattice, first, beta, _ptr(mut, C.c_double), _ptr(rm, C.c_double),
+                                     _ptr(re, C.c_long)), "get_block")
+        return mut, rm, re
+
+    def get_r_diag(self, first, count, lattice=0):
+        """get_r_exp(first+i, first+i), i < count (gso_interface.h:704-722): (mantissa, exponent)."""
+        rm = np.empty(count)
+        re = np.empty(count, np.int64)
+        _ck(_lib().b200gso_get_r_diag(self._h, lattice, first, count, _ptr(rm, C.c_double), _ptr(re, C.c_long)),
+            "get_r_diag")
+        return rm, re
+
     def upload_row(self, i, rows):
         rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(self.batch, self.n)
         _ck(_lib().b200gso_upload_row(self._h, i, _ptr(rows, C.c_int64)), "upload_row")

@@ -181,6 +181,53 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def config_size_fixtures():
+    """BASELINE.json configs #3-#5 at their stated sizes (python tests/golden/make_golden.py --configs; ~25 min of CPU):
+      #3 HLLL on latticegen q 400 200 30 b: the reference's HLLLReduction<long,double> on the full 400 x 400 basis
+         (status + output) and on the 120-row sub-lattice rows [140, 260) (a case a test can afford on every run);
+      #4 BKZ-40 on the dim-180 Goldstein-Mayer basis (latticegen q 180 1 1800 p), wrapper-LLL first (bkz.cpp:869-876),
+         no pruning => deterministic => the output basis is the known answer;
+      #5 BKZ-60 with strategies/default.json, one tour, on the LLL-reduced r200 basis: status, r(0,0) and slope."""
+    import time
+    pack = {}
+    q400 = gen(["q", 400, 200, 30, "b"], "q400.txt")
+    b400 = np.array(O.read_matrix(q400), dtype=np.int64)
+    sub = os.path.join(TMP, "q400_rows140_260.txt")
+    O.write_matrix(sub, b400[140:260])
+    for tag, inp in (("q400sub", sub), ("q400", q400)):
+        outp = os.path.join(TMP, "hlll_%s_out.txt" % tag)
+        t0 = time.time()
+        o = O.run_ref("load %s\ntolong\nhlll_long 0.99 0.51 0.001 0.1\nsave_long %s\n" % (inp, outp), timeout=7200)
+        pack[tag + "_hlll_sec"] = np.float64(time.time() - t0)
+        pack[tag + "_in"] = np.array(O.read_matrix(inp), dtype=np.int64)
+        pack[tag + "_out"] = np.array(O.read_matrix(outp), dtype=np.int64)
+        pack[tag + "_status"] = np.int32(int(o.split("hlll_long status=")[1].split()[0]))
+        print(tag, "hlll status", pack[tag + "_status"], "sec", pack[tag + "_hlll_sec"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "hlll_q400.npz"), **pack)
+    pack = {}
+    gm = gen(["q", 180, 1, 1800, "p"], "gm180.txt")
+    gml = os.path.join(TMP, "gm180_lll.txt")
+    O.run_ref("load %s\nlll 0.99 0.51 wrapper default 0\nsave %s\n" % (gm, gml), timeout=3600)
+    pack["b_in"] = np.array(O.read_matrix(gml), dtype=np.int64)
+    outp = os.path.join(TMP, "gm180_bkz40.txt")
+    t0 = time.time()
+    o = O.run_ref("load %s\nbkz 40 %d 1 none enumlib 1\nsave %s\n" % (gml, 2 | 4, outp), timeout=7200)
+    pack["bkz40_none_sec"] = np.float64(time.time() - t0)
+    pack["bkz40_none_status"] = np.int32(int(o.split("bkz status=")[1].split()[0]))
+    pack["bkz40_none_b"] = np.array(O.read_matrix(outp), dtype=np.int64)
+    print("gm180 bkz40 status", pack["bkz40_none_status"], "sec", pack["bkz40_none_sec"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "bkz_gm180.npz"), **pack)
+    g = np.load(os.path.join(HERE, "r200_lll_update_gso.npz"))
+    mat = os.path.join(TMP, "r200_red.txt")
+    O.write_matrix(mat, g["b"])
+    outp = os.path.join(TMP, "r200_bkz60.txt")
+    o = O.run_ref("load %s\nbkz 60 %d 1 default enumlib 1\nsave %s\n" % (mat, 2 | 4, outp), timeout=7200)
+    b = np.array(O.read_matrix(outp), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "bkz60_r200_ref.npz"), status=np.int32(int(o.split("bkz status=")[1].split()[0])),
+                        b_out=b)
+    print(o, flush=True)
+
+
 def enum_dual_subsol_fixtures():
     """Dual SVP enumeration and sub-solutions: block [140,170) of the LLL-reduced r200 basis, unpruned,
     through the capture hook (records what the plugin API hands an external enumerator, then the reference's own
@@ -214,5 +261,7 @@ def enum_dual_subsol_fixtures():
 if __name__ == "__main__":
     if "--dual" in sys.argv:
         enum_dual_subsol_fixtures()
+    elif "--configs" in sys.argv:
+        config_size_fixtures()
     else:
         main()

@@ -67,3 +67,14 @@ def test_bkz_output_is_lll_reduced_by_the_reference_checker(fb, tmp_path):
     p = tmp_path / "out.txt"
     O.write_matrix(str(p), b)
     assert "islll 1" in O.run_ref("load %s\nislll 0.99 0.51\n" % p)
+
+
+def test_bkz_reports_a_failing_preliminary_lll_as_status(fb):
+    """when the LLL that precedes BKZ (bkz.cpp:869-876) fails in fp64 — 62-bit entries at dimension 50 end in
+    RED_BABAI_FAILURE, in the oracle as on the device — b200bkz_reduce must return that status, not let a C++ exception
+    cross the C boundary."""
+    rng = np.random.default_rng(4)
+    b = rng.integers(-(1 << 62), 1 << 62, size=(50, 50), dtype=np.int64)
+    assert O.OracleGSO(b).lll(0.99, 0.51)["status"] == 3
+    st, stats = fb.bkz_reduction(b.copy(), fb.BKZParam(10, flags=fb.BKZ_MAX_LOOPS, max_loops=1))
+    assert st == 3

@@ -81,15 +81,6 @@ def test_shards_partition_the_tree(en):
     assert sum(p["stats"]["leaves"] for p in parts) == full["stats"]["leaves"]
 
 
-def test_dual_and_subsols_are_declined_like_enumlib(en):
-    import fplll_b200 as fb
-    z = H.gold("enum_r200_b30_unpruned.npz")
-    for fl in (en.DUAL, en.FINDSUBSOLS):
-        with pytest.raises(fb.B200Error) as e:
-            en.enumerate_svp(z["mut"], z["rdiag"], None, float(z["maxdist"]), flags=fl)
-        assert "(-5)" in str(e.value)
-
-
 def test_reference_bkz_with_the_plugin_installed(tmp_path):
     """INTEGRATION.md end to end: the UNMODIFIED reference library runs its own bkz_reduction with the device
     enumerator installed through set_external_enumerator (tests/plugin_demo.cpp + fplll_extenum_adapter.cpp).

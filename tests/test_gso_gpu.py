@@ -276,3 +276,109 @@ def test_blocked_update_gso_large_entries(fb):
                     for name in ("mu", "r"):
                         a, e = st[name][l][i, :i], s[name][i, :i]
                         assert np.all(np.abs(a - e) <= 1e-9 * np.maximum(1.0, np.abs(e))), (name, l, i)
+
+
+# ---- direct tests of the remaining C-ABI entry points (SURVEY §8 a7 and the accessors the drop-in class forwards to) ----
+
+def test_row_swap_set_r_negate_direct_vs_oracle(fb):
+    """row_swap (gso.cpp:264-287: integer rows only, bracketed by row_op_begin/end as bkz.cpp:221-263 does),
+    set_r (gso_interface.h:739-746) and negate_row_of_b (gso.h:291-297), each followed by the state comparison."""
+    rng = np.random.default_rng(71)
+    b = rng.integers(-(1 << 30), 1 << 30, size=(3, 40, 44), dtype=np.int64)
+    md = fb.MatGSO(b)
+    mos = [O.OracleGSO(b[l]) for l in range(3)]
+    assert md.update_gso().all()
+    for mo in mos:
+        assert mo.update_gso()
+    for (i, j) in ((3, 17), (39, 0), (20, 21)):
+        lo, hi = min(i, j), max(i, j)
+        md.row_op_begin(lo, hi + 1)
+        md.row_swap(i, j)
+        md.row_op_end(lo, hi + 1)
+        for mo in mos:
+            mo.row_swap(i, j)
+            mo.row_op_end(lo, hi + 1)
+        st = md.state()
+        for l, mo in enumerate(mos):
+            H.assert_state_equal(H.lattice_state(st, l), mo.state(), "row_swap(%d,%d) lattice %d" % (i, j, l))
+        assert md.update_gso().all()
+        for mo in mos:
+            assert mo.update_gso()
+    # set_r on the diagonal of a valid row (what lll.cpp:137-142 does after the Lovasz test)
+    vals = np.array([1.5, 2.25, 1e10])
+    md.set_r(12, 12, vals)
+    for l, mo in enumerate(mos):
+        mo.set_r(12, 12, float(vals[l]))
+    st = md.state()
+    for l, mo in enumerate(mos):
+        H.assert_state_equal(H.lattice_state(st, l), mo.state(), "set_r lattice %d" % l)
+    # negate_row_of_b inside a row operation
+    md.row_op_begin(7, 8)
+    md.negate_row_of_b(7)
+    md.row_op_end(7, 8)
+    st = md.state()
+    for l in range(3):
+        want = mos[l].state()["b"].copy()
+        want[7] = -want[7]
+        assert np.array_equal(st["b"][l], want)
+        assert int(st["gso_valid_cols"][l][7]) == 0
+
+
+def test_upload_row_equals_row_rewrite_plus_row_op_end(fb):
+    """b200gso_upload_row(i, rows): the host-resident-driver protocol (host rewrites b_i, ships the row): must leave
+    exactly the state of `b[i] = row; row_op_end(i, i+1)` on a fresh object."""
+    rng = np.random.default_rng(72)
+    b = rng.integers(-(1 << 25), 1 << 25, size=(2, 30, 33), dtype=np.int64)
+    md = fb.MatGSO(b)
+    assert md.update_gso().all()
+    newrow = rng.integers(-(1 << 27), 1 << 27, size=(2, 33), dtype=np.int64)
+    md.upload_row(11, newrow)
+    assert md.update_gso().all()
+    st = md.state()
+    for l in range(2):
+        b2 = b[l].copy()
+        b2[11] = newrow[l]
+        mo = O.OracleGSO(b2)
+        assert mo.update_gso()
+        H.assert_state_equal(H.lattice_state(st, l), mo.state(), "upload_row lattice %d" % l)
+
+
+def test_get_block_and_get_r_diag_vs_oracle(fb):
+    """b200gso_get_block / get_r_diag: the block view Enumeration::enumerate builds (enumerate_ext.cpp:91-148) from
+    get_mu / get_r_exp, row_expo applied."""
+    rng = np.random.default_rng(73)
+    b = rng.integers(-(1 << 40), 1 << 40, size=(2, 48, 50), dtype=np.int64)
+    md = fb.MatGSO(b)
+    assert md.update_gso().all()
+    for l in range(2):
+        mo = O.OracleGSO(b[l])
+        assert mo.update_gso()
+        s = mo.state()
+        first, beta = 9, 30
+        mut, rm, re = md.get_block(first, beta, lattice=l)
+        for k in range(beta):
+            for j in range(k + 1, beta):
+                e = int(s["row_expo"][first + j]) - int(s["row_expo"][first + k])
+                assert mut[k, j] == float(np.ldexp(s["mu"][first + j, first + k], e))
+            assert rm[k] == s["r"][first + k, first + k] and re[k] == 2 * int(s["row_expo"][first + k])
+        rm2, re2 = md.get_r_diag(0, 48, lattice=l)
+        assert np.array_equal(rm2, np.diag(s["r"])) and np.array_equal(re2, 2 * s["row_expo"])
+
+
+def test_two_live_handles_of_different_size(fb):
+    """a second, smaller handle must not lower the kernels' dynamic shared-memory limit under a larger live
+    one (the attribute is process-wide)."""
+    rng = np.random.default_rng(74)
+    big = rng.integers(-(1 << 20), 1 << 20, size=(1, 200, 201), dtype=np.int64)
+    small = rng.integers(-(1 << 20), 1 << 20, size=(1, 40, 40), dtype=np.int64)
+    mb = fb.MatGSO(big)
+    ms = fb.MatGSO(small)
+    assert ms.update_gso().all()
+    assert mb.update_gso().all()          # the larger handle, after the smaller one was created and used
+    st, _ = ms.lll(0.99, 0.51)
+    assert st[0] == 0
+    st, _ = mb.lll(0.99, 0.51)
+    assert st[0] == 0
+    mo = O.OracleGSO(big[0])
+    assert mo.lll(0.99, 0.51)["status"] == 0
+    assert np.array_equal(mb.b[0], mo.state()["b"])
