@@ -63,7 +63,7 @@ constexpr int SOL_FAST   = 8;        // ... of which this many travel with the r
 constexpr int SUB_CAP    = 1 << 14;  // improving sub-solutions of one call (findsubsols)
 constexpr int THREADS    = 128;
 constexpr int THREADS_XS = 512;      // upper bound of the CTA size of the x-in-shared-memory variant (one CTA per SM)
-constexpr int MIN_ROOTS  = 256;      // host breadth phase: grow T until at least this many roots (the device multiplies
+constexpr int MIN_ROOTS  = 128;      // host breadth phase: grow T until at least this many roots (the device multiplies
                                      // them by work splitting, a round costs one grid barrier) ...
 constexpr int MAX_ROOTS  = 1 << 15;  // ... but never beyond this (the pinned staging block is sized for it)
 constexpr int SMEM_XS_MAX = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
@@ -721,7 +721,7 @@ const Tuning &tuning()
     q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 4000000);
     q.min_roots   = (int)geti("B200_ENUM_MIN_ROOTS", MIN_ROOTS);
     // rounds with fewer tasks than warps are bound by the latency of a lone walker (~0.35 us per node): yield sooner
-    q.yield_small = (unsigned)geti("B200_ENUM_YIELD_SMALL", 64);
+    q.yield_small = (unsigned)geti("B200_ENUM_YIELD_SMALL", 8);  // BKZ-60 tour: 4.9 s -> 3.5 s of enumeration (gpurun_out/r2)
     q.trace     = getenv("B200_ENUM_TRACE");  // append one line per call to this file
     return q;
   }();

@@ -42,6 +42,27 @@ __global__ void k_init(Batch S)
   }
 }
 
+__global__ void k_init_host_basis(Batch S)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  if (lane < M_STRIDE)
+    v.meta[lane] = 0;
+  const size_t nbf = bf_size(v.d, v.n);
+  for (size_t t = lane; t < nbf; t += 32)
+    v.bf[t] = 0.0;
+  for (int i = lane; i < v.d; i += 32)
+  {
+    v.irs[i]      = v.n;
+    v.valid[i]    = 0;
+    v.row_expo[i] = 0;
+  }
+}
+
 // repack a plain row-major batch*d*n int64 buffer into the ldb-strided device basis
 __global__ void k_pack_b(Batch S, const int64_t *src)
 {
@@ -66,7 +87,7 @@ __global__ void k_unpack_b(Batch S, int64_t *dst)
   }
 }
 
-__global__ void k_discover_all(Batch S)
+__global__ void k_discover_all(Batch S, int upto)
 {
   View v;
   WarpSmem s;
@@ -74,7 +95,7 @@ __global__ void k_discover_all(Batch S)
   int lane;
   if (!warp_setup(S, v, s, lov, lane))
     return;
-  while (v.meta[M_NKR] < v.d)
+  while (v.meta[M_NKR] < upto)
     warp_discover_row(v, lane);
 }
 
@@ -241,6 +262,25 @@ __global__ void k_upload_row(Batch S, int i, const int64_t *rows)
     v.b[(size_t)i * v.ldb + c] = rows[(size_t)l * v.n + c];
   __syncwarp();
   warp_row_op_end(v, i, i + 1, lane);
+}
+
+// host-basis handles: store the uploaded floating-point row, then the invalidation half of row_op_end(i, i+1)
+__global__ void k_upload_row_fp(Batch S, int i, const double *rows, const long *expo)
+{
+  View v;
+  WarpSmem s;
+  double *lov;
+  int lane;
+  if (!warp_setup(S, v, s, lov, lane))
+    return;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = lane; c < v.n; c += 32)
+    v.bf[bf_off(i, c, v.n)] = rows[(size_t)l * v.n + c];
+  if (lane == 0)
+    v.row_expo[i] = v.row_expo_en ? (int)expo[l] : 0;
+  __syncwarp();
+  if (i < v.meta[M_NKR])
+    warp_row_op_end(v, i, i + 1, lane);
 }
 
 // dense read-back (the reference's Matrix<FT> view of the state)
@@ -433,7 +473,7 @@ int b200gso_device_count(void)
 
 int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int device)
 {
-  if (!out || batch <= 0 || d <= 0 || n <= 0 || (flags & 1))
+  if (!out || batch <= 0 || d <= 0 || n <= 0 || (flags & 1) || (flags & ~(1 | 2 | 4 | B200GSO_HOST_BASIS)))
   {
     g_err = "b200gso_create: bad arguments (GSO_INT_GRAM is not supported on the device)";
     return B200GSO_EINVAL;
@@ -455,6 +495,7 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   h->device  = device;
   Batch &S   = h->S;
   S.B = batch, S.d = d, S.n = n, S.ldb = ld_b(n), S.row_expo_en = (flags & B200GSO_ROW_EXPO) ? 1 : 0;
+  S.host_basis = (flags & B200GSO_HOST_BASIS) ? 1 : 0;
   S.b_stride       = (size_t)d * S.ldb;
   S.bf_stride      = bf_size(d, n);
   S.mu_stride      = mu_size(d);
@@ -517,7 +558,7 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row<8>, (const void *)k_update_row<6>, (const void *)k_update_row<5>,
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
-                       (const void *)k_apply_ops};
+                       (const void *)k_apply_ops,    (const void *)k_upload_row_fp, (const void *)k_init_host_basis};
   // The kernels are process-wide: the attribute is the opt-in maximum (227 KB), never this handle's own size — a
   // second, smaller handle must not lower the limit under a larger live one.
   for (const void *f : fns)
@@ -547,6 +588,18 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
     b200gso_destroy(h);
     return B200GSO_ECUDA;
   }
+  if (S.host_basis)
+  {
+    // size_increased() without an integer basis: every row spans all n columns, bf zero until uploaded
+    k_init_host_basis<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+    me = cudaStreamSynchronize(h->stream);
+    if (me != cudaSuccess)
+    {
+      g_err = std::string("b200gso_create: ") + cudaGetErrorString(me);
+      b200gso_destroy(h);
+      return B200GSO_ECUDA;
+    }
+  }
   *out = h;
   return 0;
 }
@@ -572,10 +625,21 @@ void b200gso_destroy(b200gso_t *h)
   delete h;
 }
 
+#define NO_HOST_BASIS(h_)                                                                        \
+  do                                                                                             \
+  {                                                                                              \
+    if ((h_)->S.host_basis)                                                                      \
+    {                                                                                            \
+      g_err = "this entry point needs the int64 basis on the device (handle is B200GSO_HOST_BASIS)"; \
+      return B200GSO_EINVAL;                                                                     \
+    }                                                                                            \
+  } while (0)
+
 int b200gso_set_basis_dev(b200gso_t *h, const int64_t *dev_b)
 {
   if (!h || !dev_b)
     return B200GSO_EINVAL;
+  NO_HOST_BASIS(h);
   CK(cudaSetDevice(h->device));
   dim3 g(64, h->S.B);
   k_pack_b<<<g, 256, 0, h->stream>>>(h->S, dev_b);
@@ -623,10 +687,27 @@ int b200gso_get_basis(b200gso_t *h, int64_t *b)
   return 0;
 }
 
+int b200gso_upload_row_fp(b200gso_t *h, int i, const double *bf_rows, const long *expo)
+{
+  if (!h || !bf_rows || i < 0 || i >= h->S.d || !h->S.host_basis || (h->S.row_expo_en && !expo))
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  // d_rows (batch*n int64) doubles as the staging area: same element size
+  CK(cudaMemcpyAsync(h->d_rows, bf_rows, (size_t)h->S.B * h->S.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (expo)
+    CK(cudaMemcpyAsync(h->d_ltmp, expo, (size_t)h->S.B * sizeof(long), cudaMemcpyHostToDevice, h->stream));
+  k_upload_row_fp<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, (const double *)h->d_rows,
+                                                                                   expo ? h->d_ltmp : nullptr);
+  CK(cudaStreamSynchronize(h->stream));  // host arrays may be reused by the caller
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int b200gso_upload_row(b200gso_t *h, int i, const int64_t *rows)
 {
   if (!h || !rows || i < 0 || i >= h->S.d)
     return B200GSO_EINVAL;
+  NO_HOST_BASIS(h);
   CK(cudaSetDevice(h->device));
   // stream-ordered: with pinned `rows` this returns without waiting (the caller must not reuse `rows` before the
   // next synchronising call); pageable memory makes cudaMemcpyAsync stage synchronously, which is also correct.
@@ -641,7 +722,17 @@ int b200gso_discover_all_rows(b200gso_t *h)
   if (!h)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, h->S.d);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200gso_discover_rows(b200gso_t *h, int upto)
+{
+  if (!h || upto < 0 || upto > h->S.d)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, upto);
   CK(cudaGetLastError());
   return 0;
 }
@@ -680,7 +771,7 @@ int b200gso_update_gso_blocked(b200gso_t *h, int gram_mode, int *ok)
   if (!h || (gram_mode != B200GSO_GRAM_ORDERED && gram_mode != B200GSO_GRAM_DMMA) || h->S.B > 65535)
     return B200GSO_EINVAL;
   CK(cudaSetDevice(h->device));
-  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S);
+  k_discover_all<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, h->S.d);
   const int P = n_panels(h->S.d), pairs = P * (P + 1) / 2;
   k_gram_tiles<<<dim3((pairs + 3) / 4, h->S.B), 128, 0, h->stream>>>(h->S, gram_mode);
   k_update_gso<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_compact, h->stream>>>(h->S, h->d_ok);
@@ -691,6 +782,7 @@ int b200gso_row_addmul_we(b200gso_t *h, int i, int j, const double *x, const lon
 {
   if (!h || !x || i < 0 || j < 0 || i >= h->S.d || j >= h->S.d)
     return B200GSO_EINVAL;
+  NO_HOST_BASIS(h);
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->d_tmp, x, sizeof(double) * h->S.B, cudaMemcpyHostToDevice, h->stream));
   if (expo_add)
@@ -722,6 +814,8 @@ int b200gso_row_swap(b200gso_t *h, int i, int j)
 {
   if (!h || i < 0 || j < 0 || i >= h->S.d || j >= h->S.d)
     return B200GSO_EINVAL;
+  if (h->S.host_basis)
+    return 0;  // row_swap touches the integer rows only (gso.cpp:264-287): they live on the host
   CK(cudaSetDevice(h->device));
   k_row_swap<<<grid_warps(h), WARPS_PER_CTA * 32, h->smem_bytes, h->stream>>>(h->S, i, j);
   CK(cudaGetLastError());
@@ -837,6 +931,7 @@ static int lll_dispatch(b200gso_t *h, int mode, double delta, double eta, int km
 {
   if (!h || !status)
     return B200GSO_EINVAL;
+  NO_HOST_BASIS(h);  // the device LLL does the integer row operations itself
   CK(cudaSetDevice(h->device));
   const Batch &S = h->S;
   if (kend < 0)

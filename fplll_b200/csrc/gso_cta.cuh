@@ -83,23 +83,31 @@ struct CoopShared
 };
 
 #if B200_MU_CACHE
+// The cached copy uses a column stride of 33 doubles instead of the global layout's 32: the forward substitution walks a
+// panel by columns (lanes = 32 rows of one column: consecutive addresses either way), Babai's back-substitution walks it
+// by ROWS (lanes = 32 columns of one row) — with stride 32 that is a 32-way bank conflict on every shared-memory load,
+// with 33 both directions are conflict-free.
+constexpr int MU_SS = 33;
+__host__ __device__ inline size_t mu_s_panel_base(int p) { return (size_t)(16 * MU_SS) * p * (p + 1); }
 __device__ inline const double *coop_mu_panel(const CoopShared &C, int p)
 {
-  return (p < C.mu_s_panels) ? C.mu_s + mu_panel_base(p) : C.v.mu + mu_panel_base(p);
+  return (p < C.mu_s_panels) ? C.mu_s + mu_s_panel_base(p) : C.v.mu + mu_panel_base(p);
 }
+__device__ inline int coop_mu_stride(const CoopShared &C, int p) { return (p < C.mu_s_panels) ? MU_SS : 32; }
 __device__ inline void coop_mu_store(CoopShared &C, int i, int k, double val)
 {
   C.v.mu[mu_off(i, k)] = val;
   if ((i >> 5) < C.mu_s_panels)
-    C.mu_s[mu_off(i, k)] = val;
+    C.mu_s[mu_s_panel_base(i >> 5) + (size_t)k * MU_SS + (i & 31)] = val;
 }
 __device__ inline double coop_mu_load(const CoopShared &C, int i, int k)
 {
-  return coop_mu_panel(C, i >> 5)[(size_t)k * 32 + (i & 31)];
+  return coop_mu_panel(C, i >> 5)[(size_t)k * coop_mu_stride(C, i >> 5) + (i & 31)];
 }
 #else
 // cache compiled out: the plain global-memory expressions (`v` is the operation's `const View &v = C.v`)
 #define coop_mu_panel(C_, p_) (v.mu + mu_panel_base(p_))
+#define coop_mu_stride(C_, p_) 32
 #define coop_mu_store(C_, i_, k_, val_) (v.mu[mu_off((i_), (k_))] = (val_))
 #define coop_mu_load(C_, i_, k_) (v.mu[mu_off((i_), (k_))])
 #endif
@@ -196,14 +204,15 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
   CTA_PCNT(1, pl - p0 + 1);
   CTA_PCNT(12, i);
 
-  if (w == 0)
   {
+    // bf_i is needed if any Gram entry of the row is invalid: every warp looks (the same few loads, in parallel) and the
+    // whole CTA stages the row — one element per thread instead of one warp walking it alone before everybody's barrier
     int anyn = 0;
     for (int j = j0 + lane; j <= last_j; j += 32)
       anyn |= (gfrow[j] != gfrow[j]);
     if (__any_sync(FULL, anyn))
-      warp_stage_bf_row(v, i, ncols, s.vb, lane);
-    if (lane == 0)
+      stage_bf_row(v, i, ncols, s.vb, tid, CTA_WARPS * 32);
+    if (tid == 0)
       C.flag = 1;
   }
   for (int k = tid; k < j0; k += CTA_WARPS * 32)
@@ -230,7 +239,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
         if (threadIdx.x == 0)
           CTA_PCNT(13, 32);
       }
-      a = lane_chain<true>(g, coop_mu_panel(C, p) + lane, s.rrow, 0, 32 * p0);
+      a = lane_chain<true>(g, coop_mu_panel(C, p) + lane, s.rrow, 0, 32 * p0, coop_mu_stride(C, p));
     }
     else if (p <= pl && j < j0)
       a = s.rrow[j];  // already-valid r(i,j): only broadcast in the triangle below
@@ -253,12 +262,13 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
           const int j        = 32 * sp + lane;
           const bool a_      = act[u];
           double a           = acc[u];
-          const double *tile = coop_mu_panel(C, sp) + lane + (size_t)(32 * sp) * 32;
+          const int cs       = coop_mu_stride(C, sp);
+          const double *tile = coop_mu_panel(C, sp) + lane + (size_t)(32 * sp) * cs;
           double rd          = 1.0;
           double m[8], mn[8];
 #pragma unroll
           for (int x = 0; x < 8; x++)
-            m[x] = (a_ && lane >= x) ? tile[(size_t)x * 32] : 0.0;
+            m[x] = (a_ && lane >= x) ? tile[(size_t)x * cs] : 0.0;
 #pragma unroll
           for (int q = 0; q < 4; q++)
           {
@@ -266,7 +276,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
             {
 #pragma unroll
               for (int x = 0; x < 8; x++)
-                mn[x] = (a_ && lane >= 8 * (q + 1) + x) ? tile[(size_t)(8 * (q + 1) + x) * 32] : 0.0;
+                mn[x] = (a_ && lane >= 8 * (q + 1) + x) ? tile[(size_t)(8 * (q + 1) + x) * cs] : 0.0;
             }
 #pragma unroll
             for (int x = 0; x < 8; x++)
@@ -305,7 +315,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
     {
       const int p = p0 + w + CTA_WARPS * u;
       if (p > sp && act[u])
-        acc[u] = lane_chain<true>(acc[u], coop_mu_panel(C, p) + lane, s.rrow, 32 * sp, 32 * sp + 32);
+        acc[u] = lane_chain<true>(acc[u], coop_mu_panel(C, p) + lane, s.rrow, 32 * sp, 32 * sp + 32, coop_mu_stride(C, p));
     }
   }
   if (!ok)
@@ -334,14 +344,10 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
       double g = gfrow[i];
       if (gnan)
       {
-        g = s.vb[0];
-        for (int c = 1; c < ncols; c++)
-          g = __dadd_rn(g, s.vb[c]);
+        g        = serial_chain<false, false>(s.vb[0], s.vb + 1, ncols - 1, nullptr);
         gfrow[i] = g;
       }
-      double a = g;
-      for (int k = 0; k < i; k++)
-        a = __dsub_rn(a, s.aux[k]);
+      const double a     = serial_chain<true, false>(g, s.aux, i, nullptr);
       rrow_g[i]          = a;
       coop_mu_store(C, i, i, a);  // diagonal mirror
     }
@@ -386,7 +392,7 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
         {
           double a              = val[u];
           const int kcol        = 32 * p + lane;
-          const double *tilecol = coop_mu_panel(C, p) + (size_t)kcol * 32;  // mu(32p+t, kcol) at [t]
+          const double *tilecol = coop_mu_panel(C, p) + (size_t)kcol * coop_mu_stride(C, p);  // mu(32p+t, kcol) at [t]
           unsigned nzmask       = 0;
           double tc[32];
 #pragma unroll
@@ -425,7 +431,7 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
         const int k = 32 * q + lane;
         if (q < p && q >= p_lo && k >= sr_start)
         {
-          const double *col = coop_mu_panel(C, p) + (size_t)k * 32;
+          const double *col = coop_mu_panel(C, p) + (size_t)k * coop_mu_stride(C, p);
           double a          = val[u];
           double cv[32];  // mu(32p + t, k), t = 0..31: 32 independent loads in flight
 #pragma unroll
@@ -502,10 +508,10 @@ B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
   const int hi  = min(pb, C.mu_s_panels - 1);
   for (int p = max(pa, 0); p <= hi; ++p)
   {
-    const size_t base = mu_panel_base(p);
+    // global panel [column][32 rows] -> cached panel [column][33]: both sides walk 32 consecutive rows of one column
+    const double *src = C.v.mu + mu_panel_base(p);
+    double *dst       = C.mu_s + mu_s_panel_base(p);
     const int cnt     = 32 * 32 * (p + 1);
-    const double *src = C.v.mu + base;
-    double *dst       = C.mu_s + base;
     int t = tid;
     for (; t + 7 * CTA_WARPS * 32 < cnt; t += 8 * CTA_WARPS * 32)
     {
@@ -515,10 +521,13 @@ B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
         x[u] = src[t + u * CTA_WARPS * 32];
 #pragma unroll
       for (int u = 0; u < 8; u++)
-        dst[t + u * CTA_WARPS * 32] = x[u];
+      {
+        const int q = t + u * CTA_WARPS * 32;
+        dst[(q >> 5) * MU_SS + (q & 31)] = x[u];
+      }
     }
     for (; t < cnt; t += CTA_WARPS * 32)
-      dst[t] = src[t];
+      dst[(t >> 5) * MU_SS + (t & 31)] = src[t];
   }
   cta_bar(2);
 }
@@ -600,7 +609,7 @@ B200_OPFN void cta_move_row(CoopShared &C, int old_r, int new_r, int w, int lane
   cta_bar(2);
   if (!right && new_r >= nkr && old_r < nkr && w == 0)
   {
-    const int nz = size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
+    const int nz = v.host_basis ? v.n : size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
     if (lane == 0)
     {
       v.meta[M_NKR] = nkr - 1;
@@ -658,7 +667,7 @@ __device__ inline bool lll_update_gso_row(const View &v, int i, int last_j, Warp
     if (C->mu_s_panels > 0)
     {
       __syncwarp();
-      C->mu_s[32 * lane + i] = v.mu[32 * lane + i];
+      C->mu_s[MU_SS * lane + i] = v.mu[32 * lane + i];
       __syncwarp();
     }
 #endif
@@ -684,7 +693,7 @@ template <bool COOP> __device__ inline void lll_mu_refresh_diag(CoopShared *C, i
     return;
   __syncwarp();
   if (lane == 0)
-    C->mu_s[mu_off(i, i)] = C->v.mu[mu_off(i, i)];
+    C->mu_s[mu_s_panel_base(i >> 5) + (size_t)i * MU_SS + (i & 31)] = C->v.mu[mu_off(i, i)];
   __syncwarp();
 }
 

@@ -57,6 +57,7 @@ enum
 struct View
 {
   int d, n, ldb, row_expo_en;
+  int host_basis;  // B200GSO_HOST_BASIS: b is not on the device, bf rows are uploaded by the host
   int64_t *b;
   double *bf, *mu, *r, *gf;
   int *row_expo, *valid, *irs, *meta;
@@ -67,6 +68,7 @@ struct View
 struct Batch
 {
   int B, d, n, ldb, row_expo_en;
+  int host_basis;
   int64_t *b;
   double *bf, *mu, *r, *gf, *scratch;
   int *row_expo, *valid, *irs, *meta;
@@ -75,7 +77,7 @@ struct Batch
   __host__ __device__ View view(int l) const
   {
     View v;
-    v.d = d, v.n = n, v.ldb = ldb, v.row_expo_en = row_expo_en;
+    v.d = d, v.n = n, v.ldb = ldb, v.row_expo_en = row_expo_en, v.host_basis = host_basis;
     v.b        = b + (size_t)l * b_stride;
     v.bf       = bf + (size_t)l * bf_stride;
     v.mu       = mu + (size_t)l * mu_stride;

@@ -82,7 +82,7 @@ B200_OPFN int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int 
         const long de  = v.row_expo_en ? (long)(ek - v.row_expo[k]) : 0;
         s.xs[k]        = 0.0;
         if (k >= sr_start)
-          loop_needed |= (fabs(ldexp(bm[q], (int)de)) > eta);  // get_mu, gso_interface.h:694-701
+          loop_needed |= (fabs(scale2(bm[q], de)) > eta);  // get_mu, gso_interface.h:694-701
         new_max = max(new_max, de + fexponent(bm[q]));         // get_max_mu_exp, gso_interface.cpp:88-98
       }
     }
@@ -318,20 +318,15 @@ B200_OPFN double warp_get_gram_diag(const View &v, WarpSmem &s, int i, int lane)
     const int ncols = v.meta[M_NKC];
     // stage bf_i squared (one correctly rounded product per element, in parallel): the ordered chain only adds
     const int64_t *brow = v.b + (size_t)i * v.ldb;
-    const int e         = v.row_expo_en ? -v.row_expo[i] : 0;
+    const double sc     = v.row_expo_en ? pow2d(-v.row_expo[i]) : 1.0;
     for (int c = lane; c < ncols; c += 32)
     {
-      const double f = ldexp((double)brow[c], e);
+      const double f = __dmul_rn((double)brow[c], sc);
       s.vb[c]        = __dmul_rn(f, f);
     }
     __syncwarp();
     if (lane == 0)
-    {
-      double a = s.vb[0];
-      for (int c = 1; c < ncols; c++)
-        a = __dadd_rn(a, s.vb[c]);
-      *g = a;
-    }
+      *g = serial_chain<false, false>(s.vb[0], s.vb + 1, ncols - 1, nullptr);
     __syncwarp();
     val = *g;
   }
@@ -465,19 +460,19 @@ __device__ inline int warp_lll(const View &v, WarpSmem &s, double *lov, double d
     if (lane == 0)
     {
       lov[0] = g;
-      for (int i = 1; i <= kappa; i++)
-        lov[i] = __dsub_rn(lov[i - 1], s.aux[i - 1]);
-      double thr = __dmul_rn(v.r[tri_off(kappa - 1) + kappa - 1], swap_threshold);
+      (void)serial_chain<true, true>(g, s.aux, kappa, lov);
+      // r(k-1,k-1): the diagonal mirror in mu's unused slot (gso_layout.cuh) — shared memory when that panel is cached
+      double thr = __dmul_rn(LLL_MU_LOAD(kappa - 1, kappa - 1), swap_threshold);
       if (v.row_expo_en)
-        thr = ldexp(thr, 2 * (v.row_expo[kappa - 1] - v.row_expo[kappa]));
+        thr = scale2(thr, 2 * (v.row_expo[kappa - 1] - v.row_expo[kappa]));
       if (thr > lov[kappa - 1])
       {
         int kk = kappa;
         for (kk--; kk > kappa_min; kk--)
         {
-          double t2 = __dmul_rn(v.r[tri_off(kk - 1) + kk - 1], swap_threshold);
+          double t2 = __dmul_rn(LLL_MU_LOAD(kk - 1, kk - 1), swap_threshold);
           if (v.row_expo_en)
-            t2 = ldexp(t2, 2 * (v.row_expo[kk - 1] - v.row_expo[kappa]));
+            t2 = scale2(t2, 2 * (v.row_expo[kk - 1] - v.row_expo[kappa]));
           if (t2 < lov[kk - 1])
             break;
         }

@@ -113,9 +113,9 @@ int b200gso_lll_cta_launch(b200gso *h, int mode, double delta, double eta, int k
     if (mu_smem_on)
     {
       // cache as many leading mu panels as fit into the 227 KB of the CTA
-      while (mu_panels < n_panels(S.d) && sm + mu_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
+      while (mu_panels < n_panels(S.d) && sm + mu_s_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
         mu_panels++;
-      sm += mu_panel_base(mu_panels) * sizeof(double);
+      sm += mu_s_panel_base(mu_panels) * sizeof(double);
     }
 #else
 #define LLL_CTA_EXTRA_ARG

@@ -57,6 +57,29 @@ __device__ inline void lower_clean(const View &v, int idx, int lane)
 // FP_NR<double>::exponent, nr_FP_d.inl:44
 __device__ inline long fexponent(double x) { return (long)ilogb(x) + 1; }
 
+// ---- exact power-of-two arithmetic without the math library --------------------------------------------------------
+// ldexp / frexp / ilogb are 10-20 instruction library routines; on the one-lattice critical paths (Babai's rounding,
+// update_bf, the staging of bf_i) they were a large part of every serial step.  For the operand ranges of this code
+// they reduce to exponent-field arithmetic: multiplying a double by 2^e (|e| < 1000) is exact whenever the result is a
+// normal number and rounds exactly like ldexp when it is not, and the exponent of a normal number is a bit field.
+__device__ inline double pow2d(int e)  // 2^e, |e| <= 1022
+{
+  return __longlong_as_double((long long)(e + 1023) << 52);
+}
+__device__ inline double scale2(double x, long e)  // == ldexp(x, e)
+{
+  if (e > -1000 && e < 1000)
+    return __dmul_rn(x, pow2d((int)e));
+  return ldexp(x, (int)e);
+}
+// exponent of FP_NR<double>::exponent() for a NORMAL non-zero x (ilogb(x) + 1); callers handle 0 / subnormals
+__device__ inline int fexp_normal(double x) { return (int)((__double_as_longlong(x) >> 52) & 0x7ff) - 1022; }
+__device__ inline bool is_normal_nz(double x)
+{
+  const int be = (int)((__double_as_longlong(x) >> 52) & 0x7ff);
+  return be != 0 && be != 0x7ff;
+}
+
 // FP_NR<double>::get_si_exp_we, nr_FP_d.inl:46-53
 __device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
 {
@@ -64,10 +87,10 @@ __device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
     expo = 0;
   else
   {
-    long e = fexponent(x) + expo_add - 63;
+    long e = (is_normal_nz(x) ? (long)fexp_normal(x) : fexponent(x)) + expo_add - 63;
     expo   = e > 0 ? e : 0;
   }
-  return (long)ldexp(x, (int)(expo_add - expo));
+  return (long)scale2(x, expo_add - expo);
 }
 
 // FP_NR<double>::rnd_we, nr_FP_d.inl:226-233 (rint = round-half-even)
@@ -75,9 +98,63 @@ __device__ inline double rnd_we(double x, long expo_add)
 {
   if (expo_add == 0 && fabs(x) < 4503599627370496.0)  // |x| < 2^52: both branches below reduce to rint(x)
     return rint(x);
+  if (is_normal_nz(x) && expo_add > -1000 && expo_add < 1000)
+  {
+    if (fexp_normal(x) + expo_add >= 53)
+      return x;
+    // x * 2^e is exact (or, far below 1, rounds to something rint sends to zero exactly as ldexp's result would be);
+    // an integer times 2^-e is exact
+    return __dmul_rn(rint(__dmul_rn(x, pow2d((int)expo_add))), pow2d((int)-expo_add));
+  }
   if (fexponent(x) + expo_add >= 53)
     return x;
   return ldexp(rint(ldexp(x, (int)expo_add)), (int)-expo_add);
+}
+
+// One thread's ordered chain  a = a (+|-) x[0] (+|-) x[1] ... over n shared-memory values, optionally recording every
+// prefix (out[t + 1] = value after x[t]).  The adds are a dependent chain (8 cycles each); the loads are not — they are
+// fetched 8 at a time ahead of the adds, so a step costs the add latency instead of a shared-memory round trip (29
+// cycles) it would cost in a plain loop where the compiler cannot move the loads across the prefix stores.
+template <bool SUB, bool PREFIX> __device__ inline double serial_chain(double a, const double *x, int n, double *out)
+{
+  int t = 0;
+  double cur[8], nxt[8];
+  if (n >= 8)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      cur[u] = x[u];
+  }
+  for (; t + 8 <= n; t += 8)
+  {
+    const bool more = t + 16 <= n;
+    if (more)
+    {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        nxt[u] = x[t + 8 + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+    {
+      a = SUB ? __dsub_rn(a, cur[u]) : __dadd_rn(a, cur[u]);
+      if (PREFIX)
+        out[t + u + 1] = a;
+    }
+    if (more)
+    {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        cur[u] = nxt[u];
+    }
+  }
+  for (; t < n; t++)
+  {
+    a = SUB ? __dsub_rn(a, x[t]) : __dadd_rn(a, x[t]);
+    if (PREFIX)
+      out[t + 1] = a;
+  }
+  return a;
 }
 
 // MatGSO::update_bf(i), gso.cpp:24-48 for Z_NR<long> (get_f_exp = frexp((double)x), nr_Z_misc.inl:17-22)
@@ -87,21 +164,19 @@ B200_OPFN void warp_update_bf(const View &v, int i, int lane)
   const int64_t *brow = v.b + (size_t)i * v.ldb;
   if (v.row_expo_en)
   {
+    // frexp((double)x) = (f, e) with e = 0 for x = 0, else the exponent field; ldexp(f, e - mx) = (double)x * 2^-mx
+    // exactly (|x| < 2^63, mx <= 64: never near the ends of the exponent range)
     int mx = INT_MIN;
     for (int c = lane; c < n; c += 32)
     {
-      int e;
-      (void)frexp((double)brow[c], &e);
-      mx = max(mx, e);
+      const double f = (double)brow[c];
+      mx = max(mx, f == 0.0 ? 0 : fexp_normal(f));
     }
     for (int o = 16; o; o >>= 1)
       mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    const double sc = pow2d(-mx);
     for (int c = lane; c < n; c += 32)
-    {
-      int e;
-      double f               = frexp((double)brow[c], &e);
-      v.bf[bf_off(i, c, v.n)] = ldexp(f, e - mx);
-    }
+      v.bf[bf_off(i, c, v.n)] = __dmul_rn((double)brow[c], sc);
     if (lane == 0)
       v.row_expo[i] = mx;
   }
@@ -144,12 +219,24 @@ __device__ inline void warp_discover_row(const View &v, int lane)
 // re-derived from the contiguous int64 row instead: update_bf (gso.cpp:24-48) stores frexp/ldexp of (double)b(i,c),
 // which is exactly (double)b(i,c) * 2^-row_expo[i] (power-of-two scaling is exact), hence bit-identical.
 // Precondition (the reference's !in_row_op_range(i) assert, gso.h:316): row_op_end has run since b[i] last changed.
+__device__ inline void stage_bf_row(const View &v, int i, int ncols, double *vb, int first, int step)
+{
+  if (v.host_basis)
+  {
+    // no integer mirror on the device: gather the row from the panel layout (one 256-byte-strided load per column)
+    const double *bfrow = v.bf + bf_off(i, 0, v.n);
+    for (int c = first; c < ncols; c += step)
+      vb[c] = bfrow[(size_t)c * 32];
+    return;
+  }
+  const int64_t *brow = v.b + (size_t)i * v.ldb;
+  const double sc     = v.row_expo_en ? pow2d(-v.row_expo[i]) : 1.0;  // row_expo in [0, 64]: exact scaling
+  for (int c = first; c < ncols; c += step)
+    vb[c] = __dmul_rn((double)brow[c], sc);
+}
 __device__ inline void warp_stage_bf_row(const View &v, int i, int ncols, double *vb, int lane)
 {
-  const int64_t *brow = v.b + (size_t)i * v.ldb;
-  const int e         = v.row_expo_en ? -v.row_expo[i] : 0;
-  for (int c = lane; c < ncols; c += 32)
-    vb[c] = ldexp((double)brow[c], e);
+  stage_bf_row(v, i, ncols, vb, lane, 32);
 }
 
 // One lane's ordered chain  acc = acc (+|-) col[k] * vec[k]  for k = k0 .. k1-1 (ascending, two roundings per step):
@@ -158,7 +245,8 @@ __device__ inline void warp_stage_bf_row(const View &v, int i, int ncols, double
 // is one 256-byte line); vec lives in shared memory.  Loads are double-buffered 8 deep: the kernel is bound by HBM
 // latency x bytes in flight (profiles/), so the next group is always requested before the current one is consumed.
 template <bool SUB>
-__device__ inline double lane_chain(double acc, const double *__restrict__ col, const double *vec, int k0, int k1)
+__device__ inline double lane_chain(double acc, const double *__restrict__ col, const double *vec, int k0, int k1,
+                                    const int cs = 32 /* column stride of the panel: 32 in HBM */)
 {
   const int ng = (k1 - k0) >> 3;
   double x[8], y[8];
@@ -166,7 +254,7 @@ __device__ inline double lane_chain(double acc, const double *__restrict__ col, 
   {
 #pragma unroll
     for (int u = 0; u < 8; u++)
-      x[u] = col[(size_t)(k0 + u) * 32];
+      x[u] = col[(size_t)(k0 + u) * cs];
   }
   for (int g = 0; g < ng; g += 2)
   {
@@ -175,7 +263,7 @@ __device__ inline double lane_chain(double acc, const double *__restrict__ col, 
     {
 #pragma unroll
       for (int u = 0; u < 8; u++)
-        y[u] = col[(size_t)(k + 8 + u) * 32];
+        y[u] = col[(size_t)(k + 8 + u) * cs];
     }
 #pragma unroll
     for (int u = 0; u < 8; u++)
@@ -187,7 +275,7 @@ __device__ inline double lane_chain(double acc, const double *__restrict__ col, 
     {
 #pragma unroll
       for (int u = 0; u < 8; u++)
-        x[u] = col[(size_t)(k + 16 + u) * 32];
+        x[u] = col[(size_t)(k + 16 + u) * cs];
     }
     if (g + 1 < ng)
     {
@@ -201,7 +289,7 @@ __device__ inline double lane_chain(double acc, const double *__restrict__ col, 
   }
   for (int k = k0 + 8 * ng; k < k1; k++)
   {
-    const double t = __dmul_rn(col[(size_t)k * 32], vec[k]);
+    const double t = __dmul_rn(col[(size_t)k * cs], vec[k]);
     acc            = SUB ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
   }
   return acc;
@@ -333,9 +421,7 @@ B200_OPFN bool warp_update_gso_row(const View &v, int i, int last_j, WarpSmem &s
           g = __dadd_rn(g, __dmul_rn(s.vb[c], s.vb[c]));
         gfrow[i] = g;
       }
-      double acc = g;
-      for (int k = 0; k < i; k++)
-        acc = __dsub_rn(acc, s.aux[k]);
+      const double acc   = serial_chain<true, false>(g, s.aux, i, nullptr);
       rrow_g[i]          = acc;
       v.mu[mu_off(i, i)] = acc;  // diagonal mirror
     }
@@ -353,7 +439,8 @@ B200_OPFN void warp_row_op_end(const View &v, int first, int last, int lane)
   const int nkr = v.meta[M_NKR];
   for (int i = first; i < last; i++)
   {
-    warp_update_bf(v, i, lane);
+    if (!v.host_basis)  // host-basis handles: bf(i,.) and row_expo[i] were uploaded (b200gso_upload_row_fp)
+      warp_update_bf(v, i, lane);
     warp_invalidate_gram_row(v, i, lane);
     for (int j = i + 1 + lane; j < nkr; j += 32)
       v.gf[tri_off(j) + i] = CUDART_NAN;
@@ -529,7 +616,7 @@ B200_OPFN void warp_move_row(const View &v, int old_r, int new_r, int lane)
   __syncwarp();
   if (!right && new_r >= nkr && old_r < nkr)
   {
-    const int nz = size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
+    const int nz = v.host_basis ? v.n : size_nz_warp(v.b + (size_t)new_r * v.ldb, v.n, lane);
     if (lane == 0)
     {
       v.meta[M_NKR] = nkr - 1;

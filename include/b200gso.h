@@ -31,6 +31,11 @@ typedef struct b200gso b200gso_t;
 #define B200GSO_DEFAULT 0
 #define B200GSO_ROW_EXPO 2
 #define B200GSO_OP_FORCE_LONG 4
+/* The integer basis stays on the HOST in GMP (MatGSO<Z_NR<mpz_t>, FP_NR<double>>, the LLL stage-1 regime of
+ * wrapper.cpp:538-553): the device holds bf / row_expo and the fp64 state only.  The host does every integer row
+ * operation itself and ships the refreshed floating-point row with b200gso_upload_row_fp; the int64 entry points
+ * (set_basis, row_addmul_we, upload_row, device LLL) are rejected on such a handle. */
+#define B200GSO_HOST_BASIS 256
 
 /* RedStatus, fplll/defs.h:153-169 */
 #define B200_RED_SUCCESS 0
@@ -64,6 +69,9 @@ int b200gso_upload_row(b200gso_t *h, int i, const int64_t *rows);
 
 /* MatGSOInterface::discover_all_rows, gso_interface.h:761-765 */
 int b200gso_discover_all_rows(b200gso_t *h);
+/* discover_row() (gso.cpp:56-82) until n_known_rows == upto: what a host driver that discovers rows itself (the
+ * MatGSO forwarding shim) uses to keep the device in step. */
+int b200gso_discover_rows(b200gso_t *h, int upto);
 
 /* MatGSOInterface::update_gso_row(i, last_j), gso_interface.cpp:131-164.  ok[l] = 1/0 as the reference's bool
  * (0: a mu(i,j) is not finite -> caller reports RED_GSO_FAILURE).  ok may be NULL. */
@@ -146,6 +154,14 @@ int b200gso_time_update_row(b200gso_t *h, int i, int reps, int invalidate, float
 /* Number of lattices the update_gso_row kernel keeps resident at once on this device (SMs x CTAs/SM x warps/CTA):
  * batches that are a multiple of it run in full waves.  Negative on error. */
 int b200gso_resident_lattices(b200gso_t *h);
+
+/* Host-basis handles (B200GSO_HOST_BASIS): row i of every lattice was rewritten on the host (row_addmul_we on the
+ * mpz rows, gso.cpp:236-262) and converted there exactly as update_bf does for Z_NR<mpz_t> (mpz_get_d_2exp,
+ * gso.cpp:24-48, nr_Z_misc.inl:114-147): bf_rows[l*n + c] = mantissa of b(i,c) scaled by 2^-row_expo, expo[l] = the
+ * row's exponent (0 without GSO_ROW_EXPO).  The device stores the row and does the rest of row_op_end(i, i+1)
+ * (gso_interface.cpp:32-53): Gram row / column and GSO row invalidated, validity of later rows lowered.
+ * A never-seen row (i >= n_known_rows) may be uploaded before it is discovered. */
+int b200gso_upload_row_fp(b200gso_t *h, int i, const double *bf_rows, const long *expo);
 
 /* Profiling builds only (-DB200_LLL_PROFILE): device-clock phase counters of the last LLL call of this process
  * (update_gso_row, Babai rest, Lovasz, move_row+set_r, gather/scan, back-substitution, integer rows, row_op_end).

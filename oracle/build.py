@@ -29,6 +29,11 @@ def build_ref(jobs=8):
     if not fresh:
         subprocess.check_call(["make", "-f", os.path.join(HERE, "Makefile.ref"), "-j%d" % jobs, "all"],
                               cwd=HERE, stdout=subprocess.DEVNULL)
+    # the reference's own test programs (run under the MatGSO shim by tests/test_shim_gpu.py)
+    if not all(os.path.exists(os.path.join(HERE, "_ref", t)) for t in ("test_lll", "test_gso", "test_bkz")):
+        subprocess.check_call(["make", "-f", os.path.join(HERE, "Makefile.ref"), "-j%d" % jobs,
+                               os.path.join(HERE, "_ref", "test_lll"), os.path.join(HERE, "_ref", "test_gso"),
+                               os.path.join(HERE, "_ref", "test_bkz")], cwd=HERE, stdout=subprocess.DEVNULL)
     return os.path.join(HERE, "_ref")
 
 

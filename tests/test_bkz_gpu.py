@@ -78,3 +78,44 @@ def test_bkz_reports_a_failing_preliminary_lll_as_status(fb):
     assert O.OracleGSO(b).lll(0.99, 0.51)["status"] == 3
     st, stats = fb.bkz_reduction(b.copy(), fb.BKZParam(10, flags=fb.BKZ_MAX_LOOPS, max_loops=1))
     assert st == 3
+
+
+def test_bkz40_on_dim180_goldstein_mayer_equals_reference(fb):
+    """BASELINE config #4 at its stated size: BKZ-40 on the wrapper-LLL-reduced latticegen q 180 1 1800 p basis, one
+    tour, no pruning => deterministic: the device driver must end on the reference's own output basis
+    (tests/golden/bkz_gm180.npz; 57 s for the reference on one host thread)."""
+    z = H.gold("bkz_gm180.npz")
+    b = z["b_in"].copy()
+    st, stats = fb.bkz_reduction(b, fb.BKZParam(40, flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS, max_loops=1))
+    assert st == int(z["bkz40_none_status"]) == 8
+    assert np.array_equal(b, z["bkz40_none_b"])
+
+
+def _profile_quality(b):
+    r = gso_profile(b)
+    n = len(r)
+    x = np.arange(n) - (n - 1) / 2
+    slope = float((x * np.log(r)).sum() / (n * (n * n - 1) / 12))
+    logpot = float((np.arange(n, 0, -1) * np.log(r)).sum())
+    return r[0], slope, logpot
+
+
+def test_bkz60_default_strategies_on_dim200_one_tour_quality(fb):
+    """BASELINE config #5 at its stated size: one tour of BKZ-60 with strategies/default.json on the LLL-reduced
+    latticegen r 200 2000 basis.  Pruned BKZ rerandomises (different generators here and in the reference), so the
+    gate is the reference's own outcome on the same input (tests/golden/bkz60_r200_ref.npz): same status, GSO slope
+    within 1 %, at least 97 % of its drop of the log-potential, and a shorter first vector than before."""
+    g = H.gold("r200_lll_update_gso.npz")
+    ref = H.gold("bkz60_r200_ref.npz")
+    r0_in, slope_in, pot_in = _profile_quality(g["b"])
+    r0_ref, slope_ref, pot_ref = _profile_quality(ref["b_out"])
+    b = g["b"].copy()
+    st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
+                                                max_loops=1))
+    assert st == int(ref["status"]) == 8
+    r0, slope, pot = _profile_quality(b)
+    assert abs(slope - slope_ref) <= 0.01 * abs(slope_ref), (slope, slope_ref)
+    assert pot_in - pot >= 0.97 * (pot_in - pot_ref), (pot_in, pot, pot_ref)
+    assert r0 < r0_in
+    # the output is still a basis of the same lattice: |det| of the Gram matrix is unchanged (sum of log r_ii)
+    assert abs(np.log(gso_profile(b)).sum() - np.log(gso_profile(g["b"])).sum()) < 1e-6 * 200

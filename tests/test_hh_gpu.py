@@ -124,3 +124,15 @@ def test_device_hlll_needs_history():
     m = MatHouseholder(H.gold("hlll_long.npz")["u40_in"], 5, keep_history=False)
     with pytest.raises(B200Error):
         m.hlll()
+
+
+def test_hlll_config3_sublattice_of_q400(fb=None):
+    """BASELINE config #3 shape (latticegen q 400 200 30 b, n = 400 columns): the whole device hlll() loop on the
+    120-row sub-lattice rows [140, 260) ends on the basis of the reference's HLLLReduction<long,double>
+    (tests/golden/hlll_q400.npz; the reference's own run on all 400 rows ends in status 10 after 260 s of CPU —
+    fp64 is not enough there, make_golden.py --configs)."""
+    import fplll_b200
+    z = H.gold("hlll_q400.npz")
+    out, st = fplll_b200.hlll_reduction(z["q400sub_in"].copy())
+    assert st == int(z["q400sub_status"]) == 0
+    assert np.array_equal(out, z["q400sub_out"])

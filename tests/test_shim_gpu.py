@@ -1,0 +1,81 @@
+"""GPU tests of the MatGSO forwarding shim (fplll_b200/csrc/fplll_matgso_shim.cpp): the UNMODIFIED
+reference library and its unmodified callers (LLLReduction, BKZReduction, the reference's own test programs) run
+with libb200fplll.so preloaded, so every MatGSO<Z_NR<long>|Z_NR<mpz_t>, FP_NR<double>>::update_gso_row executes on the
+B200.  The device GSO is bit-exact, so results must be byte-identical to the plain runs."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "tests", "_build", "libb200fplll.so")
+DEMO = os.path.join(ROOT, "tests", "_build", "shim_demo")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _need(*paths):
+    for p in paths:
+        if not os.path.exists(p):
+            pytest.skip("%s not built (needs the reference headers: built in the development container)" % p)
+
+
+def _run(cmd, preload, timeout=900):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    if preload:
+        env["LD_PRELOAD"] = SHIM
+        env["B200_SHIM_STATS"] = "1"
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=str(os.path.dirname(cmd[-1]) or "."))
+
+
+def _stat(text, key):
+    return int(text.split(key + "=")[1].split()[0])
+
+
+@pytest.mark.parametrize("mode", ["long", "mpz"])
+def test_reference_lll_over_the_device_gso_is_byte_identical(tmp_path, mode):
+    """LLLReduction<ZT, FP_NR<double>>::lll() of the unmodified reference over its own MatGSO object, plain and with the
+    shim preloaded: same status, same basis, same mu / r / row_expo bits; the preloaded run forwarded its updates.
+    long: BASELINE config #1 (latticegen u 40 40-bit basis); mpz: a 400-bit knapsack basis that does not fit int64, the
+    regime where B stays in GMP on the host (GSO_ROW_EXPO | GSO_OP_FORCE_LONG, wrapper.cpp:538-553)."""
+    _need(SHIM, DEMO, os.path.join(REF, "libfplll.so"))
+    inp = str(tmp_path / "in.txt")
+    if mode == "long":
+        O.write_matrix(inp, H.gold("u40_lll_long.npz")["b_in"])
+    else:
+        open(inp, "w").write(O.latticegen(["r", 30, 400]))
+    outs = []
+    for preload in (False, True):
+        out = str(tmp_path / ("out%d.bin" % preload))
+        p = _run([DEMO, inp, mode, out], preload)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert "status=0" in p.stdout, p.stdout
+        fwd = _stat(p.stdout, "forwarded")
+        assert (fwd > 0) == preload, p.stdout
+        if preload:
+            assert _stat(p.stdout, "adopted") >= 1 and _stat(p.stdout, "uploads") > 0
+        outs.append((open(out, "rb").read(), open(out + ".basis").read()))
+    assert outs[0][1] == outs[1][1], "basis differs"
+    assert outs[0][0] == outs[1][0], "mu / r / row_expo differ"
+
+
+@pytest.mark.parametrize("prog", ["test_gso", "test_lll", "test_bkz"])
+def test_reference_test_programs_pass_over_the_device_gso(prog):
+    """The reference's own tests/test_gso.cpp, test_lll.cpp and test_bkz.cpp (compiled unmodified by oracle/Makefile.ref)
+    with the shim preloaded: 'All tests passed.' and at least one MatGSO object ran on the device."""
+    exe = os.path.join(REF, prog)
+    _need(SHIM, exe)
+    p = _run([exe], True, timeout=1500)
+    assert p.returncode == 0, (p.stdout[-500:], p.stderr[-1500:])
+    assert "All tests passed." in p.stdout
+    line = [l for l in p.stderr.splitlines() if "b200 MatGSO shim" in l][-1]
+    adopted = int(line.split("adopted ")[1].split()[0])
+    forwarded = int(line.split("forwarded ")[1].split(",")[0])
+    if prog != "test_gso":  # test_gso only builds GSOs over mpfr / with integer Gram matrices: nothing to adopt
+        assert adopted >= 1 and forwarded > 0, line
