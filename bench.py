@@ -37,6 +37,16 @@ def alg_bytes_update_row(i, n, g=1):
     return 8 * ((i + 1) * n * g + i * (i - 1) // 2 + 4 * (i + 1))
 
 
+def ncu_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k_update_row from the committed ncu capture, if it was
+    taken at this batch size (else None)."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "update_row_ncu_traffic.json")))
+        return j["dram_bytes_per_launch"] if int(j["batch"]) == int(batch) else None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -79,6 +89,30 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_info():
+    """CPU model, online cores and NUMA nodes of the box: the reference arm swings with the host (round 1: 5.9x between
+    two boxes), so the ratio can only be read next to this."""
+    info = {"cores_online": os.cpu_count()}
+    try:
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout
+        for line in out.splitlines():
+            k, _, v = line.partition(":")
+            k, v = k.strip(), v.strip()
+            if k == "Model name":
+                info["cpu_model"] = v
+            elif k == "NUMA node(s)":
+                info["numa_nodes"] = int(v)
+            elif k == "Thread(s) per core":
+                info["threads_per_core"] = int(v)
+            elif k == "CPU max MHz":
+                info["cpu_max_mhz"] = float(v)
+        la = os.getloadavg()
+        info["loadavg_1m"] = la[0]
+    except Exception:
+        pass
+    return info
+
+
 def cpu_reference(seconds_target=12.0):
     """Times the reference's own CPU path (oracle/_ref) on all host threads: the same step on dim-200 lattices."""
     import numpy as np
@@ -106,7 +140,7 @@ def cpu_reference(seconds_target=12.0):
     return {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "reference",
             "sample": "%d calls of {row_op_end(%d,%d); update_gso_row(%d)} on %d private dim-%d MatGSO<long,double> "
                       "objects, %d threads, %.1f s" % (calls, KAPPA, KAPPA + 1, KAPPA, cores * per, D, cores, t),
-            "us_per_call_per_thread": t / (calls / cores) * 1e6}
+            "us_per_call_per_thread": t / (calls / cores) * 1e6, "host": host_info()}
 
 
 def enum_extras(local):
@@ -201,7 +235,10 @@ def bkz_extras(local, devices=None, with_ref=True):
                 break
         out = {"workload": "BKZ-60, 1 tour, default strategies, dim-200 knapsack (LLL-reduced latticegen r 200 2000)",
                "devices": len(devices or [local]), "attempts": attempts,
-               "status": int(st), "wall_seconds": attempts[-1]["wall_seconds"], "sec_lll_sizered": stats["sec_lll"],
+               # every attempt counts: the honest cost of one successful tour is the sum (a retry happens only when fp64
+               # BKZ ends in RED_BABAI_FAILURE, which the reference's own run does for 2 of 5 seeds on this basis)
+               "status": int(st), "wall_seconds": sum(a_["wall_seconds"] for a_ in attempts),
+               "wall_seconds_last_attempt": attempts[-1]["wall_seconds"], "sec_lll_sizered": stats["sec_lll"],
                "sec_enum": stats["sec_enum"], "enum_nodes": int(stats["enum_nodes"]), "enum_calls": int(stats["enum_calls"]),
                "r00_before": stats["r00_before"], "r00_after": stats["r00_after"], "slope_after": stats["slope_after"]}
         from oracle import oracle as O
@@ -410,9 +447,10 @@ def main():
                            "algorithmic_bytes_per_lattice": per_lat},
                 "roofline": {"bound": "hbm", "kernel": "k_update_row (update_gso_row, g=1)", "achieved": kern_gbps,
                              "peak": peak, "unit": "GB/s", "frac": kern_gbps / peak, "peak_source": peak_src,
-                             # dram__bytes_read+write of one launch under `ncu --set full` at this batch size
-                             # (profiles/r1_update_row_ncu_summary.txt, shipped default = the l2f32 capture)
-                             "traffic": 2.990e9 if B == 5920 else None, "ms_per_launch": ms_update},
+                             # dram__bytes_read+write of one launch: not measurable inside an unprofiled run; the
+                             # figure of the committed `ncu --set full` capture of this kernel at this batch size
+                             "traffic": ncu_traffic(B), "traffic_source": "profiles/update_row_ncu_traffic.json",
+                             "ms_per_launch": ms_update},
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s / a.steps * 1e3},
                 "gpu_launches": 2 * a.steps, "clocks": clocks}

@@ -25,7 +25,13 @@
 // the device cannot hold (GSO_INT_GRAM, MatGSOGram, d > 512) keep the reference's path untouched.  There is no CPU
 // fallback for an adopted object: a CUDA failure throws.
 //
-// Build (where fplll's headers are installed):  g++ -shared -fPIC fplll_matgso_shim.cpp -lb200gso -ldl  -> libb200fplll.so
+// On top of that, BKZReduction<Z_NR<long>, FP_NR<double>>::bkz() (bkz.cpp:522-672) — what bkz_reduction() / `fplll -a bkz`
+// run after their wrapper-LLL when the basis fits long (bkz.cpp:812-836) — is taken over whole by the device driver
+// (b200bkz_reduce: device-resident LLL loops, device enumeration, no per-call forwarding) whenever the request is one
+// that driver implements (plain BKZ, no transformation matrices, no GSO dump); SD-BKZ / slide reduction keep the
+// reference's control flow over the forwarded GSO.  B200_SHIM_BKZ=0 turns the take-over off.
+//
+// Build (where fplll's headers are installed):  g++ -shared -fPIC fplll_matgso_shim.cpp -lb200bkz -ldl  -> libb200fplll.so
 // Use:  LD_PRELOAD=libb200fplll.so fplll -a bkz -b 40 ...   or link it before -lfplll.   B200_SHIM_STATS=1 prints the
 // forwarded-call counters at exit; B200_SHIM_DISABLE=1 turns the forwarding off.
 #include <fplll/fplll.h>
@@ -40,7 +46,10 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../include/b200bkz.h"
 #include "../../include/b200gso.h"
+
+extern "C" long b200_matgso_shim_bkz_taken(void);
 
 namespace b200shim {
 
@@ -78,8 +87,8 @@ struct AtExit
   {
     if (getenv("B200_SHIM_STATS"))
       fprintf(stderr, "b200 MatGSO shim: adopted %ld objects (declined %ld), update_gso_row forwarded %ld, rows uploaded %ld, "
-                      "move_row %ld, set_r %ld\n",
-              g_adopted, g_declined, g_updates, g_uploads, g_moves, g_setr);
+                      "move_row %ld, set_r %ld, bkz() on the device driver %ld\n",
+              g_adopted, g_declined, g_updates, g_uploads, g_moves, g_setr, b200_matgso_shim_bkz_taken());
     for (auto &kv : g_tab)
       if (kv.second.h)
         b200gso_destroy(kv.second.h);
@@ -160,6 +169,23 @@ inline void shim_upload_row(Entry &e, int i, MatGSO<Z_NR<mpz_t>, FP_NR<double>> 
   b200shim::g_uploads++;
 }
 
+// adoption: the whole basis.  long: b200gso_set_basis = size_increased() on the device (init_row_size, bf, metadata);
+// mpz: the floating-point rows size_increased() converted on the host, one by one.
+inline void shim_initial_basis(Entry &e, MatGSO<Z_NR<long>, FP_NR<double>> &m, Guts<Z_NR<long>> &)
+{
+  std::vector<int64_t> flat((size_t)e.d * e.n);
+  for (int i = 0; i < e.d; i++)
+    for (int c = 0; c < e.n; c++)
+      flat[(size_t)i * e.n + c] = m.b(i, c).get_si();
+  b200shim::ck(b200gso_set_basis(e.h, flat.data()), "set_basis");
+  b200shim::g_uploads += e.d;
+}
+inline void shim_initial_basis(Entry &e, MatGSO<Z_NR<mpz_t>, FP_NR<double>> &m, Guts<Z_NR<mpz_t>> &g)
+{
+  for (int i = 0; i < e.d; i++)
+    shim_upload_row(e, i, m, g);
+}
+
 template <class ZT> Entry *shim_entry(Guts<ZT> &g)
 {
   if (!b200shim::enabled())
@@ -204,8 +230,7 @@ template <class ZT> Entry *shim_entry(Guts<ZT> &g)
   }
   e.dev_valid.assign(e.d, 0);
   e.row_mu.resize(e.d), e.row_r.resize(e.d), e.irow.resize(e.n), e.frow.resize(e.n);
-  for (int i = 0; i < e.d; i++)  // the basis as the host has it now (mpz: the rows size_increased() converted)
-    shim_upload_row(e, i, *m, g);
+  shim_initial_basis(e, *m, g);  // the basis as the host has it now
   b200shim::g_adopted++;
   Entry &slot = b200shim::g_tab[g.self] = e;
   return &slot;
@@ -338,6 +363,74 @@ B200_SHIM_CTOR_FOR(Z_NR<long>)
 B200_SHIM_CTOR_FOR(Z_NR<mpz_t>)
 
 FPLLL_END_NAMESPACE
+
+// ---- BKZReduction<Z_NR<long>, FP_NR<double>>::bkz() on the device driver -------------------------------------------------
+FPLLL_BEGIN_NAMESPACE
+namespace {
+long g_bkz_taken = 0;
+}
+template <> bool BKZReduction<Z_NR<long>, FP_NR<double>>::bkz()
+{
+  typedef bool (*fn_t)(BKZReduction<Z_NR<long>, FP_NR<double>> *);
+  static fn_t orig = b200shim::next_symbol<fn_t>("_ZN5fplll12BKZReductionINS_4Z_NRIlEENS_5FP_NRIdEEE3bkzEv");
+  static const bool takeover = b200shim::enabled() && !(getenv("B200_SHIM_BKZ") && atoi(getenv("B200_SHIM_BKZ")) == 0);
+  auto *mg = dynamic_cast<MatGSO<Z_NR<long>, FP_NR<double>> *>(&m);
+  const int unsupported = BKZ_SD_VARIANT | BKZ_SLD_RED | BKZ_DUMP_GSO;
+  if (!takeover || !mg || (param.flags & unsupported) || mg->enable_int_gram || mg->enable_transform ||
+      param.block_size < 2 || num_rows != mg->b.get_rows() || num_rows > 512 || b200gso_device_count() == 0)
+    return orig(this);
+  const int d = mg->b.get_rows(), n = mg->b.get_cols();
+  b200bkz_t *h = nullptr;
+  int dev0     = 0;
+  if (b200bkz_create(&h, &dev0, 1) != 0)
+    throw std::runtime_error(std::string("b200 shim: b200bkz_create: ") + b200bkz_last_error());
+  // Strategy table (bkz_param.h:34-66): preprocessing block sizes and pruning vectors per block size
+  for (size_t bs = 0; bs < param.strategies.size(); bs++)
+  {
+    const Strategy &st = param.strategies[bs];
+    if (st.pruning_parameters.empty() && st.preprocessing_block_sizes.empty())
+      continue;
+    std::vector<int> pre(st.preprocessing_block_sizes.begin(), st.preprocessing_block_sizes.end());
+    std::vector<double> gh, ex, co;
+    for (const PruningParams &pp : st.pruning_parameters)
+    {
+      if (pp.coefficients.size() != bs)
+        continue;  // the default PruningParams() of an EmptyStrategy carries no vector: "no pruning"
+      gh.push_back(pp.gh_factor), ex.push_back(pp.expectation);
+      co.insert(co.end(), pp.coefficients.begin(), pp.coefficients.end());
+    }
+    b200bkz_add_strategy(h, (int)bs, pre.data(), (int)pre.size(), gh.data(), ex.data(), co.data(), (int)gh.size());
+  }
+  b200bkz_param p;
+  b200bkz_default_param(&p, param.block_size);
+  p.delta = param.delta, p.flags = (param.flags & (BKZ_VERBOSE | BKZ_MAX_LOOPS | BKZ_MAX_TIME | BKZ_BOUNDED_LLL |
+                                                   BKZ_AUTO_ABORT | BKZ_GH_BND)) | B200BKZ_NO_LLL;
+  p.max_loops = param.max_loops, p.max_time = param.max_time;
+  p.auto_abort_scale = param.auto_abort_scale, p.auto_abort_max_no_dec = param.auto_abort_max_no_dec;
+  p.gh_factor = param.gh_factor, p.min_success_probability = param.min_success_probability;
+  p.rerandomization_density = param.rerandomization_density;
+  std::vector<int64_t> flat((size_t)d * n);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      flat[(size_t)i * n + j] = mg->b(i, j).get_si();
+  b200bkz_stats stt;
+  const int rc = b200bkz_reduce(h, d, n, flat.data(), &p, &stt);
+  b200bkz_destroy(h);
+  if (rc != 0)
+    throw std::runtime_error(std::string("b200 shim: b200bkz_reduce: ") + b200bkz_last_error());
+  // the reduced basis back into the caller's matrix; its GSO object is told through the reference's own protocol
+  m.row_op_begin(0, d);
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < n; j++)
+      mg->b(i, j) = (long)flat[(size_t)i * n + j];
+  m.row_op_end(0, d);
+  nodes = (long)stt.enum_nodes;
+  g_bkz_taken++;
+  return set_status(stt.status);
+}
+FPLLL_END_NAMESPACE
+
+extern "C" long b200_matgso_shim_bkz_taken(void) { return fplll::g_bkz_taken; }
 
 extern "C" void b200_matgso_shim_stats(long *out6)
 {

@@ -101,7 +101,8 @@ __device__ inline int *meta_scratch(const Batch &S, double *lov) { return (int *
 __host__ __device__ inline size_t cta_smem_doubles(int d, int n)
 {
   const size_t per = WarpSmem::doubles(d, n) + (size_t)((d + 2 + 1) & ~1) + ((((MetaCache::ints(d) + 1) >> 1) + 1) & ~(size_t)1);
-  return per + ((sizeof(CoopShared) + 15) / 16) * 2 + (size_t)((d + 32 + 1) & ~1);
+  // scratch | CoopShared | bm[d+32] | pub[2 (d+32)]  (the mu cache follows, gso_lll_cta_api.cu)
+  return per + ((sizeof(CoopShared) + 15) / 16) * 2 + 3 * (size_t)((d + 32 + 1) & ~1);
 }
 
 }  // namespace

@@ -78,9 +78,34 @@ struct CoopShared
   double *mu_s;
   int mu_s_panels;
 #endif
+  // Streamed wavefronts (the pl - p0 < CTA_WARPS branch of cta_update_gso_row, cta_backsub_stream): pub[2k] = value of
+  // column (row) k, pub[2k+1] = its tag (epoch + k), written with ONE 16-byte store so a reader sees both or neither.
+  // The owner of a panel publishes every value the moment it is final; the warps of the later panels consume them in
+  // order while the owner is still in its 32-step triangle, instead of waiting at a barrier for the whole triangle and
+  // then applying 32 columns at once — the critical path becomes the chain of dependent steps itself.
+  double *pub;
+  double epoch;
   int cmd, a0, a1, a2;
   int flag;
 };
+
+__device__ inline void pub_store(double *slot, double val, double tag)
+{
+  asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(slot)), "d"(val),
+               "d"(tag)
+               : "memory");
+}
+// spin until the slot carries this operation's tag (all lanes read the same address: one broadcast load per poll)
+__device__ inline double pub_wait(const double *slot, double tag)
+{
+  double val, t;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+  do
+  {
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(t) : "r"(a) : "memory");
+  } while (t != tag);
+  return val;
+}
 
 #if B200_MU_CACHE
 // The cached copy uses a column stride of 33 doubles instead of the global layout's 32: the forward substitution walks a
@@ -125,6 +150,7 @@ __device__ inline void coop_post(CoopShared *C, int cmd, int a0, int a1, int a2,
   {
     C->cmd = cmd;
     C->a0 = a0, C->a1 = a1, C->a2 = a2;
+    C->epoch += 4096.0;  // a fresh tag range for the values this operation publishes
   }
   __syncwarp();
   cta_bar(1);
@@ -184,6 +210,46 @@ __device__ inline double lane_dot_deep(const double *__restrict__ col, const dou
   return acc;
 }
 
+// The closing part of update_gso_row(i, last_j) for the CTA: the diagonal r(i,i) = g(i,i) - sum_{k<i} mu(i,k) r(i,k)
+// (products in parallel, one ordered subtraction chain) when it is asked for, then gso_valid_cols[i].
+__device__ inline bool cta_update_diag(CoopShared &C, int i, int last_j, int j0, int ncols, int tid)
+{
+  const View &v = C.v;
+  WarpSmem &s   = C.s;
+  double *gfrow = v.gf + tri_off(i), *rrow_g = v.r + tri_off(i);
+  CTA_PT(tp2_);
+  if (last_j >= i)
+  {
+    for (int k = tid; k < min(j0, i); k += CTA_WARPS * 32)
+      s.murow[k] = coop_mu_load(C, i, k);
+    cta_bar(2);
+    for (int k = tid; k < i; k += CTA_WARPS * 32)
+      s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
+    const bool gnan = (gfrow[i] != gfrow[i]);  // then s.vb holds bf_i: square it in place, the chain below only adds
+    if (gnan)
+      for (int c = tid; c < ncols; c += CTA_WARPS * 32)
+        s.vb[c] = __dmul_rn(s.vb[c], s.vb[c]);
+    cta_bar(2);
+    if (tid == 0)
+    {
+      double g = gfrow[i];
+      if (gnan)
+      {
+        g        = serial_chain<false, false>(s.vb[0], s.vb + 1, ncols - 1, nullptr);
+        gfrow[i] = g;
+      }
+      const double a     = serial_chain<true, false>(g, s.aux, i, nullptr);
+      rrow_g[i]          = a;
+      coop_mu_store(C, i, i, a);  // diagonal mirror
+    }
+  }
+  if (tid == 0)
+    v.valid[i] = last_j + 1;
+  cta_bar(2);
+  CTA_PADD(4, tp2_);
+  return true;
+}
+
 // ---- UPDATE ---------------------------------------------------------------------------------------------------------
 // update_gso_row(i, last_j) for a row that is already discovered and has valid[i] <= last_j (the master checks both).
 // Same arithmetic as warp_update_gso_row: lane l of panel p owns column j = 32p + l,
@@ -218,6 +284,107 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
   for (int k = tid; k < j0; k += CTA_WARPS * 32)
     s.rrow[k] = rrow_g[k];
   cta_bar(2);
+
+  if (pl - p0 < CTA_WARPS)
+  {
+    // ---- streamed wavefront: one panel per warp, values handed on through C.pub as they become final ----
+    const int p    = p0 + w;
+    const int j    = 32 * p + lane;
+    const bool own = p <= pl;
+    const bool a_  = own && j >= j0 && j <= jl;
+    const int cs   = own ? coop_mu_stride(C, p) : 32;
+    const double *mup = own ? coop_mu_panel(C, p) + lane : v.mu;
+    double a = 0.0;
+    if (a_)
+    {
+      double g = gfrow[j];
+      if (g != g)
+      {
+        g        = lane_dot_deep(v.bf + bf_off(j, 0, n), s.vb, ncols);
+        gfrow[j] = g;
+        if (threadIdx.x == 0)
+          CTA_PCNT(13, 32);
+      }
+      a = lane_chain<true>(g, mup, s.rrow, 0, 32 * p0, cs);
+    }
+    else if (own && j < j0)
+      a = s.rrow[j];  // already-valid r(i,j): published for the later panels, broadcast in the triangle
+    CTA_PADD(2, tp0_);
+    CTA_PT(tps_);
+    bool ok = true;
+    if (own)
+    {
+      const double tb = C.epoch;
+      // columns of the earlier panels, in order, as their owners publish them
+      for (int k = 32 * p0; k < 32 * p; k += 8)
+      {
+        double m[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          m[u] = a_ ? mup[(size_t)(k + u) * cs] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+        {
+          const double rk = pub_wait(C.pub + 2 * (k + u), tb + (double)(k + u));
+          if (a_)
+            a = __dsub_rn(a, __dmul_rn(m[u], rk));
+        }
+      }
+      // my triangle: column 32 p + t is final in lane t once steps 0..t-1 are applied — published at once
+      const double *tile = mup + (size_t)(32 * p) * cs;
+      double rd          = 1.0;
+      double m[8], mn[8];
+#pragma unroll
+      for (int x = 0; x < 8; x++)
+        m[x] = (a_ && lane >= x) ? tile[(size_t)x * cs] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+      {
+        if (q < 3)
+        {
+#pragma unroll
+          for (int x = 0; x < 8; x++)
+            mn[x] = (a_ && lane >= 8 * (q + 1) + x) ? tile[(size_t)(8 * (q + 1) + x) * cs] : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+        {
+          const int t = 8 * q + x;
+          if (lane == t)
+          {
+            rd = m[x];
+            pub_store(C.pub + 2 * (32 * p + t), a, tb + (double)(32 * p + t));
+          }
+          if (t < 31)
+          {
+            const double rk = __shfl_sync(FULL, a, t);
+            if (a_ && lane > t)
+              a = __dsub_rn(a, __dmul_rn(m[x], rk));
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+          m[x] = mn[x];
+      }
+      if (a_)
+      {
+        rrow_g[j]       = a;
+        s.rrow[j]       = a;
+        const double mm = __ddiv_rn(a, rd);
+        coop_mu_store(C, i, j, mm);
+        s.murow[j]      = mm;
+        if (!isfinite(mm))
+          ok = false;
+      }
+    }
+    if (!ok)
+      C.flag = 0;
+    cta_bar(2);
+    CTA_PADD(3, tps_);
+    if (!C.flag)
+      return false;
+    return cta_update_diag(C, i, last_j, j0, ncols, tid);
+  }
 
   // Gram entries + the part of every chain that only needs the already-valid r(i, k), k < 32 p0
   double acc[CTA_OWN];
@@ -324,39 +491,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
   CTA_PADD(3, tp1_);
   if (!C.flag)
     return false;
-  CTA_PT(tp2_);
-
-  if (last_j >= i)
-  {
-    // diagonal r(i,i) = g(i,i) - sum_{k<i} mu(i,k) r(i,k): products in parallel, one ordered subtraction chain
-    for (int k = tid; k < min(j0, i); k += CTA_WARPS * 32)
-      s.murow[k] = coop_mu_load(C, i, k);
-    cta_bar(2);
-    for (int k = tid; k < i; k += CTA_WARPS * 32)
-      s.aux[k] = __dmul_rn(s.murow[k], s.rrow[k]);
-    const bool gnan = (gfrow[i] != gfrow[i]);  // then s.vb holds bf_i: square it in place, the chain below only adds
-    if (gnan)
-      for (int c = tid; c < ncols; c += CTA_WARPS * 32)
-        s.vb[c] = __dmul_rn(s.vb[c], s.vb[c]);
-    cta_bar(2);
-    if (tid == 0)
-    {
-      double g = gfrow[i];
-      if (gnan)
-      {
-        g        = serial_chain<false, false>(s.vb[0], s.vb + 1, ncols - 1, nullptr);
-        gfrow[i] = g;
-      }
-      const double a     = serial_chain<true, false>(g, s.aux, i, nullptr);
-      rrow_g[i]          = a;
-      coop_mu_store(C, i, i, a);  // diagonal mirror
-    }
-  }
-  if (tid == 0)
-    v.valid[i] = last_j + 1;
-  cta_bar(2);
-  CTA_PADD(4, tp2_);
-  return true;
+  return cta_update_diag(C, i, last_j, j0, ncols, tid);
 }
 
 // ---- BACKSUB --------------------------------------------------------------------------------------------------------
@@ -372,6 +507,60 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
   CTA_PT(tb0_);
   CTA_PCNT(5, 1);
   CTA_PCNT(6, p_hi - p_lo + 1);
+  if (p_hi - p_lo < CTA_WARPS)
+  {
+    // ---- streamed: warp w owns panel q = p_hi - w; every X_j is published the moment it is rounded and the lower panels
+    // apply row j while the owner goes on to row j-1 (see CoopShared::pub) ----
+    const int q    = p_hi - w;
+    const bool own = q >= p_lo;
+    if (own)
+    {
+      const int k       = 32 * q + lane;
+      const bool colact = k >= sr_start && k < sr_end;
+      double a          = (k < sr_end) ? C.bm[k] : 0.0;
+      const double tb   = C.epoch;
+      // rows of the panels above mine, descending, as their owners publish X_j
+      for (int j = sr_end - 1; j >= 32 * (q + 1); --j)
+      {
+        const int pj   = j >> 5;
+        const double m = colact ? coop_mu_panel(C, pj)[(size_t)k * coop_mu_stride(C, pj) + (j & 31)] : 0.0;
+        const double X = pub_wait(C.pub + 2 * j, tb + (double)j);
+        if (X != 0.0 && colact)
+          a = __dsub_rn(a, __dmul_rn(X, m));
+      }
+      // my triangle
+      const double *tilecol = coop_mu_panel(C, q) + (size_t)k * coop_mu_stride(C, q);  // mu(32q+t, k) at [t]
+      unsigned nzmask       = 0;
+      double tc[32];
+#pragma unroll
+      for (int t = 0; t < 32; t++)
+        tc[t] = (t > lane && 32 * q + t < sr_end) ? tilecol[t] : 0.0;
+#pragma unroll
+      for (int t = 31; t >= 0; --t)
+      {
+        const int j = 32 * q + t;
+        if (j >= sr_end || j < sr_start)
+          continue;
+        const double bj = __shfl_sync(FULL, a, t);
+        const long de   = v.row_expo_en ? (long)(ek - v.row_expo[j]) : 0;
+        const double X  = rnd_we(bj, de);
+        if (lane == 0)
+          pub_store(C.pub + 2 * j, X, tb + (double)j);
+        if (X == 0.0)
+          continue;
+        nzmask |= 1u << t;
+        if (lane == 0)
+          s.xs[j] = X;
+        if (lane < t && k >= sr_start)
+          a = __dsub_rn(a, __dmul_rn(X, tc[t]));
+      }
+      if (lane == 0)
+        xmask[q] = nzmask;
+    }
+    cta_bar(2);
+    CTA_PADD(7, tb0_);
+    return;
+  }
   // panel q is owned by warp (p_hi - q) % CTA_WARPS, slot (p_hi - q) / CTA_WARPS
   double val[CTA_OWN];
 #pragma unroll

@@ -36,12 +36,17 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
     C->v = v;
     C->s = s;
     C->bm = bm;
+    C->pub = bm + (size_t)((S.d + 32 + 1) & ~1);
+    C->epoch = 4096.0;
 #if B200_MU_CACHE
-    C->mu_s = bm + (size_t)((S.d + 32 + 1) & ~1);
+    C->mu_s = bm + 3 * (size_t)((S.d + 32 + 1) & ~1);
     C->mu_s_panels = mu_panels;
 #endif
     C->cmd = COOP_EXIT, C->flag = 1;
   }
+  // no slot of the publish array may look like a published value: tags start at 4096
+  for (int t = lane; t < 2 * ((S.d + 32 + 1) & ~1); t += 32)
+    bm[(size_t)((S.d + 32 + 1) & ~1) + t] = -1.0;
   __syncwarp();
 #if B200_MU_CACHE
   if (mu_panels > 0)

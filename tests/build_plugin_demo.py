@@ -39,10 +39,10 @@ def build_shim():
            "-I/root/reference/fplll"]
     lib = os.path.join(bdir, "libb200fplll.so")
     src = os.path.join(ROOT, "fplll_b200", "csrc", "fplll_matgso_shim.cpp")
-    deps = [src, os.path.join(ROOT, "include", "b200gso.h")]
+    deps = [src, os.path.join(ROOT, "include", "b200gso.h"), os.path.join(ROOT, "include", "b200bkz.h")]
     if not (os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in deps)):
         subprocess.check_call(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-pthread"] + inc + [src, "-o", lib,
-                              "-L" + os.path.join(ROOT, "fplll_b200", "lib"), "-lb200gso", "-ldl",
+                              "-L" + os.path.join(ROOT, "fplll_b200", "lib"), "-lb200bkz", "-ldl",
                               "-Wl,-rpath,$ORIGIN/../../fplll_b200/lib"])
     exe = os.path.join(bdir, "shim_demo")
     dsrc = os.path.join(ROOT, "tests", "shim_demo.cpp")

@@ -31,7 +31,7 @@ def _run(cmd, preload, timeout=900):
     if preload:
         env["LD_PRELOAD"] = SHIM
         env["B200_SHIM_STATS"] = "1"
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=str(os.path.dirname(cmd[-1]) or "."))
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
 
 
 def _stat(text, key):
@@ -65,17 +65,51 @@ def test_reference_lll_over_the_device_gso_is_byte_identical(tmp_path, mode):
     assert outs[0][0] == outs[1][0], "mu / r / row_expo differ"
 
 
-@pytest.mark.parametrize("prog", ["test_gso", "test_lll", "test_bkz"])
-def test_reference_test_programs_pass_over_the_device_gso(prog):
+_SLOW = pytest.mark.skipif(not os.environ.get("B200_TEST_SLOW"),
+                           reason="the reference's test_bkz takes 4-5 minutes per run with every update_gso_row forwarded "
+                                  "(260 s measured, profiles/r2_shim_reference_tests.txt): set B200_TEST_SLOW=1")
+
+
+@pytest.mark.parametrize("prog,bkz_takeover", [("test_gso", 1), ("test_lll", 1),
+                                               pytest.param("test_bkz", 0, marks=_SLOW),
+                                               pytest.param("test_bkz", 1, marks=_SLOW)])
+def test_reference_test_programs_pass_over_the_device_gso(prog, bkz_takeover, monkeypatch):
     """The reference's own tests/test_gso.cpp, test_lll.cpp and test_bkz.cpp (compiled unmodified by oracle/Makefile.ref)
-    with the shim preloaded: 'All tests passed.' and at least one MatGSO object ran on the device."""
+    with the shim preloaded: 'All tests passed.' and at least one MatGSO object ran on the device.  test_bkz runs twice:
+    with the reference's BKZ control flow over the forwarded GSO (B200_SHIM_BKZ=0) and with BKZReduction::bkz() taken over
+    by the device driver."""
     exe = os.path.join(REF, prog)
     _need(SHIM, exe)
+    monkeypatch.setenv("B200_SHIM_BKZ", str(bkz_takeover))
     p = _run([exe], True, timeout=1500)
     assert p.returncode == 0, (p.stdout[-500:], p.stderr[-1500:])
-    assert "All tests passed." in p.stdout
+    assert "All tests passed." in p.stderr  # the reference's tests report on stderr (tests/test_lll.cpp:175)
     line = [l for l in p.stderr.splitlines() if "b200 MatGSO shim" in l][-1]
     adopted = int(line.split("adopted ")[1].split()[0])
     forwarded = int(line.split("forwarded ")[1].split(",")[0])
-    if prog != "test_gso":  # test_gso only builds GSOs over mpfr / with integer Gram matrices: nothing to adopt
-        assert adopted >= 1 and forwarded > 0, line
+    assert adopted >= 1 and forwarded > 0, line
+    if prog == "test_bkz":
+        taken = int(line.split("device driver ")[1].split()[0])
+        assert (taken > 0) == bool(bkz_takeover), line
+
+
+def test_reference_cli_bkz_with_the_shim_preloaded(tmp_path):
+    """`fplll -a bkz -b 20 -f double` (the reference's unmodified command-line program) on the dim-60 q-ary basis, plain
+    and with libb200fplll.so preloaded: without pruning BKZ is deterministic, so both runs must print the same basis —
+    the reference's own output (tests/golden/bkz_q60.npz) — and the preloaded one ran bkz() on the device driver."""
+    cli = os.path.join(REF, "fplll")
+    _need(SHIM, cli)
+    z = H.gold("bkz_q60.npz")
+    inp = str(tmp_path / "in.txt")
+    O.write_matrix(inp, z["b_in"])
+    outs = []
+    for preload in (False, True):
+        p = _run([cli, "-a", "bkz", "-b", "20", "-f", "double", inp], preload)
+        assert p.returncode == 0, p.stderr[-1500:]
+        if preload:
+            line = [l for l in p.stderr.splitlines() if "b200 MatGSO shim" in l][-1]
+            assert int(line.split("device driver ")[1].split()[0]) >= 1, line
+        open(str(tmp_path / "o.txt"), "w").write(p.stdout)
+        outs.append(np.array(O.read_matrix(str(tmp_path / "o.txt")), dtype=np.int64))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[1], z["bkz20_none_b"])
