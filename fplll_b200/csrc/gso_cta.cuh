@@ -114,6 +114,23 @@ __device__ inline double pub_wait(const double *slot, double tag)
 // with 33 both directions are conflict-free.
 constexpr int MU_SS = 33;
 __host__ __device__ inline size_t mu_s_panel_base(int p) { return (size_t)(16 * MU_SS) * p * (p + 1); }
+struct MuRef  // the (cached | global) mu panels as seen by one operation: copied out of CoopShared once, into registers
+{
+  const double *mu_s, *mu_g;
+  int panels;
+  __device__ inline const double *panel(int p) const
+  {
+    return (p < panels) ? mu_s + mu_s_panel_base(p) : mu_g + mu_panel_base(p);
+  }
+  __device__ inline int stride(int p) const { return (p < panels) ? MU_SS : 32; }
+  __device__ inline double load(int i, int k) const { return panel(i >> 5)[(size_t)k * stride(i >> 5) + (i & 31)]; }
+};
+__device__ inline MuRef mu_ref(const CoopShared &C)
+{
+  MuRef m;
+  m.mu_s = C.mu_s, m.mu_g = C.v.mu, m.panels = C.mu_s_panels;
+  return m;
+}
 __device__ inline const double *coop_mu_panel(const CoopShared &C, int p)
 {
   return (p < C.mu_s_panels) ? C.mu_s + mu_s_panel_base(p) : C.v.mu + mu_panel_base(p);
@@ -135,6 +152,19 @@ __device__ inline double coop_mu_load(const CoopShared &C, int i, int k)
 #define coop_mu_stride(C_, p_) 32
 #define coop_mu_store(C_, i_, k_, val_) (v.mu[mu_off((i_), (k_))] = (val_))
 #define coop_mu_load(C_, i_, k_) (v.mu[mu_off((i_), (k_))])
+struct MuRef
+{
+  const double *mu_g;
+  __device__ inline const double *panel(int p) const { return mu_g + mu_panel_base(p); }
+  __device__ inline int stride(int) const { return 32; }
+  __device__ inline double load(int i, int k) const { return mu_g[mu_off(i, k)]; }
+};
+__device__ inline MuRef mu_ref(const CoopShared &C)
+{
+  MuRef m;
+  m.mu_g = C.v.mu;
+  return m;
+}
 #endif
 
 __device__ inline void cta_bar(int id)
@@ -214,8 +244,8 @@ __device__ inline double lane_dot_deep(const double *__restrict__ col, const dou
 // (products in parallel, one ordered subtraction chain) when it is asked for, then gso_valid_cols[i].
 __device__ inline bool cta_update_diag(CoopShared &C, int i, int last_j, int j0, int ncols, int tid)
 {
-  const View &v = C.v;
-  WarpSmem &s   = C.s;
+  const View v     = C.v;  // by value: registers, not a reload from shared memory after every store
+  const WarpSmem s = C.s;
   double *gfrow = v.gf + tri_off(i), *rrow_g = v.r + tri_off(i);
   CTA_PT(tp2_);
   if (last_j >= i)
@@ -256,8 +286,8 @@ __device__ inline bool cta_update_diag(CoopShared &C, int i, int last_j, int j0,
 //   acc_j = g(i,j); acc_j -= mu(j,k) r(i,k) for k = 0 .. j-1 ascending.
 B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int lane)
 {
-  const View &v = C.v;
-  WarpSmem &s   = C.s;
+  const View v     = C.v;  // by value: registers, not a reload from shared memory after every store
+  const WarpSmem s = C.s;
   const int tid = threadIdx.x;
   const int j0  = max(0, v.valid[i]);
   const int ncols = v.meta[M_NKC], n = v.n;
@@ -292,8 +322,10 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
     const int j    = 32 * p + lane;
     const bool own = p <= pl;
     const bool a_  = own && j >= j0 && j <= jl;
-    const int cs   = own ? coop_mu_stride(C, p) : 32;
-    const double *mup = own ? coop_mu_panel(C, p) + lane : v.mu;
+    const MuRef M  = mu_ref(C);
+    double *pub    = C.pub;
+    const int cs   = own ? M.stride(p) : 32;
+    const double *mup = own ? M.panel(p) + lane : v.mu;
     double a = 0.0;
     if (a_)
     {
@@ -325,7 +357,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
 #pragma unroll
         for (int u = 0; u < 8; u++)
         {
-          const double rk = pub_wait(C.pub + 2 * (k + u), tb + (double)(k + u));
+          const double rk = pub_wait(pub + 2 * (k + u), tb + (double)(k + u));
           if (a_)
             a = __dsub_rn(a, __dmul_rn(m[u], rk));
         }
@@ -353,7 +385,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
           if (lane == t)
           {
             rd = m[x];
-            pub_store(C.pub + 2 * (32 * p + t), a, tb + (double)(32 * p + t));
+            pub_store(pub + 2 * (32 * p + t), a, tb + (double)(32 * p + t));
           }
           if (t < 31)
           {
@@ -499,8 +531,8 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
 // babai_mu (columns < sr_end); the X_j land in s.xs[j], the per-panel masks of the non-zero ones in xmask[].
 B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, int w, int lane)
 {
-  const View &v = C.v;
-  WarpSmem &s   = C.s;
+  const View v     = C.v;  // by value: registers, not a reload from shared memory after every store
+  const WarpSmem s = C.s;
   const int ek  = v.row_expo[kappa];
   unsigned *xmask = (unsigned *)(s.xs + ((v.d + 1) & ~1));
   const int p_hi = (sr_end - 1) >> 5, p_lo = sr_start >> 5;
@@ -515,42 +547,66 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
     const bool own = q >= p_lo;
     if (own)
     {
+      const MuRef M     = mu_ref(C);
+      double *pub       = C.pub;
+      const double tb   = C.epoch;
       const int k       = 32 * q + lane;
       const bool colact = k >= sr_start && k < sr_end;
       double a          = (k < sr_end) ? C.bm[k] : 0.0;
-      const double tb   = C.epoch;
       // rows of the panels above mine, descending, as their owners publish X_j
-      for (int j = sr_end - 1; j >= 32 * (q + 1); --j)
+      for (int pj = p_hi; pj > q; --pj)
       {
-        const int pj   = j >> 5;
-        const double m = colact ? coop_mu_panel(C, pj)[(size_t)k * coop_mu_stride(C, pj) + (j & 31)] : 0.0;
-        const double X = pub_wait(C.pub + 2 * j, tb + (double)j);
-        if (X != 0.0 && colact)
-          a = __dsub_rn(a, __dmul_rn(X, m));
+        const double *rowp = M.panel(pj) + (size_t)k * M.stride(pj);  // mu(32 pj + t, k) at [t]
+        for (int t = min(31, sr_end - 1 - 32 * pj); t >= 0; --t)
+        {
+          const double m = colact ? rowp[t] : 0.0;
+          const double X = pub_wait(pub + 2 * (32 * pj + t), tb + (double)(32 * pj + t));
+          if (X != 0.0 && colact)
+            a = __dsub_rn(a, __dmul_rn(X, m));
+        }
       }
-      // my triangle
-      const double *tilecol = coop_mu_panel(C, q) + (size_t)k * coop_mu_stride(C, q);  // mu(32q+t, k) at [t]
-      unsigned nzmask       = 0;
+      // my triangle.  Lane l holds the constants of ROW 32q + l: rnd_we(x, de) = rint(x * 2^de) * 2^-de for every finite
+      // x once |de| is moderate (de = 0: rint(x); |x * 2^de| >= 2^52: already an integer, the product is undone
+      // exactly = the reference's "return x" branch; tiny: rounds to zero like ldexp's result would), so every lane
+      // rounds its own value each step and the owner of row t broadcasts the result — no branches, no library calls.
+      const int jl_     = 32 * q + lane;
+      const bool rowin  = jl_ >= sr_start && jl_ < sr_end;
+      const long de_l   = (rowin && v.row_expo_en) ? (long)(ek - v.row_expo[jl_]) : 0;
+      const bool fast   = !__any_sync(FULL, rowin && (de_l <= -900 || de_l >= 900));
+      const double sc   = fast ? pow2d((int)de_l) : 1.0, isc = fast ? pow2d((int)-de_l) : 1.0;
+      const double *tilecol = M.panel(q) + (size_t)k * M.stride(q);  // mu(32q+t, k) at [t]
+      const int t_hi = min(31, sr_end - 1 - 32 * q), t_lo = max(0, sr_start - 32 * q);
+      unsigned nzmask = 0;
       double tc[32];
 #pragma unroll
       for (int t = 0; t < 32; t++)
-        tc[t] = (t > lane && 32 * q + t < sr_end) ? tilecol[t] : 0.0;
+        tc[t] = (t > lane && t <= t_hi) ? tilecol[t] : 0.0;
 #pragma unroll
       for (int t = 31; t >= 0; --t)
       {
-        const int j = 32 * q + t;
-        if (j >= sr_end || j < sr_start)
+        if (t > t_hi || t < t_lo)
           continue;
-        const double bj = __shfl_sync(FULL, a, t);
-        const long de   = v.row_expo_en ? (long)(ek - v.row_expo[j]) : 0;
-        const double X  = rnd_we(bj, de);
+        double X;
+        if (fast)
+        {
+          const double y = __dmul_rn(a, sc);
+          double xl      = __dmul_rn(rint(y), isc);
+          if (!(fabs(y) < 1e300))  // overflowed product / non-finite input: the reference's own branches
+            xl = rnd_we(a, de_l);
+          X = __shfl_sync(FULL, xl, t);
+        }
+        else
+        {
+          const double bj = __shfl_sync(FULL, a, t);
+          X               = rnd_we(bj, __shfl_sync(FULL, (int)de_l, t));
+        }
         if (lane == 0)
-          pub_store(C.pub + 2 * j, X, tb + (double)j);
+          pub_store(pub + 2 * (32 * q + t), X, tb + (double)(32 * q + t));
         if (X == 0.0)
           continue;
         nzmask |= 1u << t;
         if (lane == 0)
-          s.xs[j] = X;
+          s.xs[32 * q + t] = X;
         if (lane < t && k >= sr_start)
           a = __dsub_rn(a, __dmul_rn(X, tc[t]));
       }
@@ -644,8 +700,8 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
 // Warp w takes the column groups w, w + CTA_WARPS, ... of 32 columns.
 B200_OPFN void cta_igemv(CoopShared &C, int kappa, int nnz, int w, int lane)
 {
-  const View &v = C.v;
-  WarpSmem &s   = C.s;
+  const View v     = C.v;  // by value: registers, not a reload from shared memory after every store
+  const WarpSmem s = C.s;
   const int nc  = v.meta[M_NKC];
   CTA_PT(ti0_);
   CTA_PCNT(9, 1);
@@ -730,7 +786,7 @@ B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
 // data movement per element is the same, only who carries it differs.
 B200_OPFN void cta_move_row(CoopShared &C, int old_r, int new_r, int w, int lane)
 {
-  const View &v = C.v;
+  const View v  = C.v;
   const int tid = threadIdx.x, NT = CTA_WARPS * 32;
   if (old_r == new_r)
   {
