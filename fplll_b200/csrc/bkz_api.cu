@@ -675,6 +675,11 @@ int b200bkz_reduce(b200bkz_t *h, int d, int n, int64_t *b, const b200bkz_param *
                       "cycles; integer-row calls %lld (rows %lld) %.3g cycles\n",
               cp[0], cp[0] ? (double)cp[12] / cp[0] : 0.0, cp[1], cp[13], (double)cp[2], (double)cp[3], (double)cp[4], cp[5],
               cp[6], (double)cp[7], cp[9], cp[10], (double)cp[11]);
+      fprintf(stderr, "  streamed ops: back-substitution top-panel triangle %.3g cycles over %lld rows, bottom panel: consumer "
+                      "%.3g + triangle %.3g cycles over %lld rows; update: first-panel triangle %.3g, last panel consumer %.3g "
+                      "+ triangle %.3g; master Gram dot %.3g, prefix chain %.3g cycles\n",
+              (double)cp[8], cp[14], (double)cp[16], (double)cp[17], cp[15], (double)cp[18], (double)cp[19], (double)cp[20],
+              (double)cp[21], (double)cp[22]);
     }
 #endif
     stats->sec_other = stats->sec_total - stats->sec_enum - stats->sec_lll;

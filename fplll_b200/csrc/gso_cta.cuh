@@ -54,10 +54,25 @@ static __device__ long long g_cta_prof[32];
     if (threadIdx.x == 0)                       \
       g_cta_prof[slot] += (val);                \
   } while (0)
+// same, from whichever single thread `cond` selects (one writer per slot per operation)
+#define CTA_PADD_IF(cond, slot, t0)             \
+  do                                            \
+  {                                             \
+    if (cond)                                   \
+      g_cta_prof[slot] += clock64() - (t0);     \
+  } while (0)
+#define CTA_PCNT_IF(cond, slot, val)            \
+  do                                            \
+  {                                             \
+    if (cond)                                   \
+      g_cta_prof[slot] += (val);                \
+  } while (0)
 #else
 #define CTA_PT(var)
 #define CTA_PADD(slot, t0)
 #define CTA_PCNT(slot, val)
+#define CTA_PADD_IF(cond, slot, t0)
+#define CTA_PCNT_IF(cond, slot, val)
 #endif
 
 constexpr int CTA_WARPS = 8;
@@ -327,6 +342,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
     const int cs   = own ? M.stride(p) : 32;
     const double *mup = own ? M.panel(p) + lane : v.mu;
     double a = 0.0;
+    CTA_PT(tgd_);
     if (a_)
     {
       double g = gfrow[j];
@@ -337,7 +353,10 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
         if (threadIdx.x == 0)
           CTA_PCNT(13, 32);
       }
+      CTA_PADD(21, tgd_);
+      CTA_PT(tgp_);
       a = lane_chain<true>(g, mup, s.rrow, 0, 32 * p0, cs);
+      CTA_PADD(22, tgp_);
     }
     else if (own && j < j0)
       a = s.rrow[j];  // already-valid r(i,j): published for the later panels, broadcast in the triangle
@@ -348,6 +367,7 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
     {
       const double tb = C.epoch;
       // columns of the earlier panels, in order, as their owners publish them
+      CTA_PT(tuc_);
       for (int k = 32 * p0; k < 32 * p; k += 8)
       {
         double m[8];
@@ -362,6 +382,8 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
             a = __dsub_rn(a, __dmul_rn(m[u], rk));
         }
       }
+      CTA_PADD_IF(lane == 0 && p == pl && p != p0, 19, tuc_);
+      CTA_PT(tut_);
       // my triangle: column 32 p + t is final in lane t once steps 0..t-1 are applied — published at once
       const double *tile = mup + (size_t)(32 * p) * cs;
       double rd          = 1.0;
@@ -398,6 +420,8 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
         for (int x = 0; x < 8; x++)
           m[x] = mn[x];
       }
+      CTA_PADD_IF(lane == 0 && p == p0, 18, tut_);
+      CTA_PADD_IF(lane == 0 && p == pl && p != p0, 20, tut_);
       if (a_)
       {
         rrow_g[j]       = a;
@@ -554,6 +578,7 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
       const bool colact = k >= sr_start && k < sr_end;
       double a          = (k < sr_end) ? C.bm[k] : 0.0;
       // rows of the panels above mine, descending, as their owners publish X_j
+      CTA_PT(tcons_);
       for (int pj = p_hi; pj > q; --pj)
       {
         const double *rowp = M.panel(pj) + (size_t)k * M.stride(pj);  // mu(32 pj + t, k) at [t]
@@ -565,6 +590,8 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
             a = __dsub_rn(a, __dmul_rn(X, m));
         }
       }
+      CTA_PADD_IF(lane == 0 && q == p_lo && q != p_hi, 16, tcons_);
+      CTA_PT(ttri_);
       // my triangle.  Lane l holds the constants of ROW 32q + l: rnd_we(x, de) = rint(x * 2^de) * 2^-de for every finite
       // x once |de| is moderate (de = 0: rint(x); |x * 2^de| >= 2^52: already an integer, the product is undone
       // exactly = the reference's "return x" branch; tiny: rounds to zero like ldexp's result would), so every lane
@@ -612,6 +639,10 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
       }
       if (lane == 0)
         xmask[q] = nzmask;
+      CTA_PADD_IF(lane == 0 && q == p_hi, 8, ttri_);
+      CTA_PCNT_IF(lane == 0 && q == p_hi, 14, t_hi - t_lo + 1);
+      CTA_PADD_IF(lane == 0 && q == p_lo && q != p_hi, 17, ttri_);
+      CTA_PCNT_IF(lane == 0 && q == p_lo && q != p_hi, 15, t_hi - t_lo + 1);
     }
     cta_bar(2);
     CTA_PADD(7, tb0_);

@@ -90,43 +90,15 @@ __device__ inline bool hsetup(const HBatch &S, HView &v, double *&sR, double *&s
 
 // ascending chain over products already in shared memory: r = p[beg]; r += p[k] ... (numvect.h:385-395), lane 0, result
 // broadcast.  The products themselves were formed one per lane (each a correctly rounded multiply).
-// The adds are one dependent chain (8 cycles each on B200); the shared-memory loads are not, so they are fetched 8 at a
-// time ahead of the adds — in a plain loop every step paid the 29-cycle shared-memory round trip as well (35 cycles per
-// element measured: update_R sat at 0.19 of the HBM peak, bound by exactly this loop).
 __device__ inline double chain_sum(const double *p, int beg, int end, int lane)
 {
+  // (a register-chunked variant — loads fetched 8 ahead of the dependent adds — measured 2x SLOWER here: the kernel is
+  // bound by how many warps fit an SM, and the extra registers halved that; gpurun_out/r2/bench_v7.json)
   double r = 0.0;
   if (lane == 0)
   {
-    r     = p[beg];
-    int k = beg + 1;
-    double cur[8], nxt[8];
-    if (k + 8 <= end)
-    {
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        cur[u] = p[k + u];
-    }
-    for (; k + 8 <= end; k += 8)
-    {
-      const bool more = k + 16 <= end;
-      if (more)
-      {
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          nxt[u] = p[k + 8 + u];
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        r = __dadd_rn(r, cur[u]);
-      if (more)
-      {
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          cur[u] = nxt[u];
-      }
-    }
-    for (; k < end; k++)
+    r = p[beg];
+    for (int k = beg + 1; k < end; k++)
       r = __dadd_rn(r, p[k]);
   }
   return __shfl_sync(FULLM, r, 0);
