@@ -92,6 +92,9 @@ struct CoopShared
   // shared-memory instead of L2 latency per tile.
   double *mu_s;
   int mu_s_panels;
+  // the last panel of the lattice has only d - 32 (P-1) rows: cached with a column stride just above that (odd), so that
+  // at d = 200 (8 rows: stride 9, 16 KB instead of 59 KB) the WHOLE of mu is resident in shared memory
+  int mu_last_p, mu_last_stride;
 #endif
   // Streamed wavefronts (the pl - p0 < CTA_WARPS branch of cta_update_gso_row, cta_backsub_stream): pub[2k] = value of
   // column (row) k, pub[2k+1] = its tag (epoch + k), written with ONE 16-byte store so a reader sees both or neither.
@@ -129,33 +132,41 @@ __device__ inline double pub_wait(const double *slot, double tag)
 // with 33 both directions are conflict-free.
 constexpr int MU_SS = 33;
 __host__ __device__ inline size_t mu_s_panel_base(int p) { return (size_t)(16 * MU_SS) * p * (p + 1); }
+__host__ __device__ inline int mu_s_last_stride(int d)
+{
+  const int rows = d - 32 * (n_panels(d) - 1);
+  return rows >= 32 ? MU_SS : (rows | 1);
+}
 struct MuRef  // the (cached | global) mu panels as seen by one operation: copied out of CoopShared once, into registers
 {
   const double *mu_s, *mu_g;
-  int panels;
+  int panels, last_p, last_stride;
   __device__ inline const double *panel(int p) const
   {
     return (p < panels) ? mu_s + mu_s_panel_base(p) : mu_g + mu_panel_base(p);
   }
-  __device__ inline int stride(int p) const { return (p < panels) ? MU_SS : 32; }
+  __device__ inline int stride(int p) const { return (p < panels) ? (p == last_p ? last_stride : MU_SS) : 32; }
   __device__ inline double load(int i, int k) const { return panel(i >> 5)[(size_t)k * stride(i >> 5) + (i & 31)]; }
 };
 __device__ inline MuRef mu_ref(const CoopShared &C)
 {
   MuRef m;
-  m.mu_s = C.mu_s, m.mu_g = C.v.mu, m.panels = C.mu_s_panels;
+  m.mu_s = C.mu_s, m.mu_g = C.v.mu, m.panels = C.mu_s_panels, m.last_p = C.mu_last_p, m.last_stride = C.mu_last_stride;
   return m;
 }
 __device__ inline const double *coop_mu_panel(const CoopShared &C, int p)
 {
   return (p < C.mu_s_panels) ? C.mu_s + mu_s_panel_base(p) : C.v.mu + mu_panel_base(p);
 }
-__device__ inline int coop_mu_stride(const CoopShared &C, int p) { return (p < C.mu_s_panels) ? MU_SS : 32; }
+__device__ inline int coop_mu_stride(const CoopShared &C, int p)
+{
+  return (p < C.mu_s_panels) ? (p == C.mu_last_p ? C.mu_last_stride : MU_SS) : 32;
+}
 __device__ inline void coop_mu_store(CoopShared &C, int i, int k, double val)
 {
   C.v.mu[mu_off(i, k)] = val;
   if ((i >> 5) < C.mu_s_panels)
-    C.mu_s[mu_s_panel_base(i >> 5) + (size_t)k * MU_SS + (i & 31)] = val;
+    C.mu_s[mu_s_panel_base(i >> 5) + (size_t)k * coop_mu_stride(C, i >> 5) + (i & 31)] = val;
 }
 __device__ inline double coop_mu_load(const CoopShared &C, int i, int k)
 {
@@ -384,41 +395,24 @@ B200_OPFN bool cta_update_gso_row(CoopShared &C, int i, int last_j, int w, int l
       }
       CTA_PADD_IF(lane == 0 && p == pl && p != p0, 19, tuc_);
       CTA_PT(tut_);
-      // my triangle: column 32 p + t is final in lane t once steps 0..t-1 are applied — published at once
+      // my triangle: column 32 p + t is final in lane t once steps 0..t-1 are applied — published at once.  A ROLLED loop
+      // (the step stays in the instruction cache); the tile entry of the next column is requested one step ahead.
       const double *tile = mup + (size_t)(32 * p) * cs;
       double rd          = 1.0;
-      double m[8], mn[8];
-#pragma unroll
-      for (int x = 0; x < 8; x++)
-        m[x] = (a_ && lane >= x) ? tile[(size_t)x * cs] : 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; q++)
+      double m           = a_ ? tile[0] : 0.0;  // lane >= 0
+#pragma unroll 1
+      for (int t = 0; t < 32; ++t)
       {
-        if (q < 3)
+        const double mn = (a_ && lane >= t + 1 && t < 31) ? tile[(size_t)(t + 1) * cs] : 0.0;
+        if (lane == t)
         {
-#pragma unroll
-          for (int x = 0; x < 8; x++)
-            mn[x] = (a_ && lane >= 8 * (q + 1) + x) ? tile[(size_t)(8 * (q + 1) + x) * cs] : 0.0;
+          rd = m;  // r(j,j), mirrored in the mu(j,j) slot of the diagonal tile
+          pub_store(pub + 2 * (32 * p + t), a, tb + (double)(32 * p + t));
         }
-#pragma unroll
-        for (int x = 0; x < 8; x++)
-        {
-          const int t = 8 * q + x;
-          if (lane == t)
-          {
-            rd = m[x];
-            pub_store(pub + 2 * (32 * p + t), a, tb + (double)(32 * p + t));
-          }
-          if (t < 31)
-          {
-            const double rk = __shfl_sync(FULL, a, t);
-            if (a_ && lane > t)
-              a = __dsub_rn(a, __dmul_rn(m[x], rk));
-          }
-        }
-#pragma unroll
-        for (int x = 0; x < 8; x++)
-          m[x] = mn[x];
+        const double rk = __shfl_sync(FULL, a, t);
+        if (a_ && lane > t)
+          a = __dsub_rn(a, __dmul_rn(m, rk));
+        m = mn;
       }
       CTA_PADD_IF(lane == 0 && p == p0, 18, tut_);
       CTA_PADD_IF(lane == 0 && p == pl && p != p0, 20, tut_);
@@ -603,23 +597,23 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
       const double sc   = fast ? pow2d((int)de_l) : 1.0, isc = fast ? pow2d((int)-de_l) : 1.0;
       const double *tilecol = M.panel(q) + (size_t)k * M.stride(q);  // mu(32q+t, k) at [t]
       const int t_hi = min(31, sr_end - 1 - 32 * q), t_lo = max(0, sr_start - 32 * q);
+      const bool upd = k >= sr_start;
       unsigned nzmask = 0;
-      double tc[32];
-#pragma unroll
-      for (int t = 0; t < 32; t++)
-        tc[t] = (t > lane && t <= t_hi) ? tilecol[t] : 0.0;
-#pragma unroll
-      for (int t = 31; t >= 0; --t)
+      // A ROLLED loop: the step is ~20 instructions that stay in the instruction cache; the tile entry of the next row
+      // is requested one step ahead (a shared-memory load when the panel is cached, and every panel of a d <= 200 lattice
+      // is), so it is off the critical path  round -> shuffle -> multiply -> subtract.
+      double m = (t_hi > lane && t_hi >= t_lo) ? tilecol[t_hi] : 0.0;
+#pragma unroll 1
+      for (int t = t_hi; t >= t_lo; --t)
       {
-        if (t > t_hi || t < t_lo)
-          continue;
+        const double mn = (t - 1 > lane && t - 1 >= t_lo) ? tilecol[t - 1] : 0.0;
         double X;
         if (fast)
         {
           const double y = __dmul_rn(a, sc);
           double xl      = __dmul_rn(rint(y), isc);
           if (!(fabs(y) < 1e300))  // overflowed product / non-finite input: the reference's own branches
-            xl = rnd_we(a, de_l);
+            xl = rnd_we_slow(a, de_l);
           X = __shfl_sync(FULL, xl, t);
         }
         else
@@ -629,13 +623,15 @@ B200_OPFN void cta_backsub(CoopShared &C, int kappa, int sr_end, int sr_start, i
         }
         if (lane == 0)
           pub_store(pub + 2 * (32 * q + t), X, tb + (double)(32 * q + t));
-        if (X == 0.0)
-          continue;
-        nzmask |= 1u << t;
-        if (lane == 0)
-          s.xs[32 * q + t] = X;
-        if (lane < t && k >= sr_start)
-          a = __dsub_rn(a, __dmul_rn(X, tc[t]));
+        if (X != 0.0)
+        {
+          nzmask |= 1u << t;
+          if (lane == 0)
+            s.xs[32 * q + t] = X;
+          if (lane < t && upd)
+            a = __dsub_rn(a, __dmul_rn(X, m));
+        }
+        m = mn;
       }
       if (lane == 0)
         xmask[q] = nzmask;
@@ -784,9 +780,12 @@ B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
   const int hi  = min(pb, C.mu_s_panels - 1);
   for (int p = max(pa, 0); p <= hi; ++p)
   {
-    // global panel [column][32 rows] -> cached panel [column][33]: both sides walk 32 consecutive rows of one column
+    // global panel [column][32 rows] -> cached panel [column][stride]: both sides walk the rows of one column; the
+    // partial last panel keeps only its real rows
     const double *src = C.v.mu + mu_panel_base(p);
     double *dst       = C.mu_s + mu_s_panel_base(p);
+    const int cs      = coop_mu_stride(C, p);
+    const int rows    = (p == C.mu_last_p) ? C.v.d - 32 * p : 32;
     const int cnt     = 32 * 32 * (p + 1);
     int t = tid;
     for (; t + 7 * CTA_WARPS * 32 < cnt; t += 8 * CTA_WARPS * 32)
@@ -794,16 +793,18 @@ B200_OPFN void cta_mu_load(CoopShared &C, int pa, int pb, int w, int lane)
       double x[8];
 #pragma unroll
       for (int u = 0; u < 8; u++)
-        x[u] = src[t + u * CTA_WARPS * 32];
+        x[u] = ((t & 31) < rows) ? src[t + u * CTA_WARPS * 32] : 0.0;  // (t + u * 256) & 31 == t & 31
 #pragma unroll
       for (int u = 0; u < 8; u++)
       {
         const int q = t + u * CTA_WARPS * 32;
-        dst[(q >> 5) * MU_SS + (q & 31)] = x[u];
+        if ((q & 31) < rows)
+          dst[(q >> 5) * cs + (q & 31)] = x[u];
       }
     }
     for (; t < cnt; t += CTA_WARPS * 32)
-      dst[(t >> 5) * MU_SS + (t & 31)] = src[t];
+      if ((t & 31) < rows)
+        dst[(t >> 5) * cs + (t & 31)] = src[t];
   }
   cta_bar(2);
 }
@@ -943,7 +944,7 @@ __device__ inline bool lll_update_gso_row(const View &v, int i, int last_j, Warp
     if (C->mu_s_panels > 0)
     {
       __syncwarp();
-      C->mu_s[MU_SS * lane + i] = v.mu[32 * lane + i];
+      C->mu_s[coop_mu_stride(*C, 0) * lane + i] = v.mu[32 * lane + i];
       __syncwarp();
     }
 #endif
@@ -969,7 +970,7 @@ template <bool COOP> __device__ inline void lll_mu_refresh_diag(CoopShared *C, i
     return;
   __syncwarp();
   if (lane == 0)
-    C->mu_s[mu_s_panel_base(i >> 5) + (size_t)i * MU_SS + (i & 31)] = C->v.mu[mu_off(i, i)];
+    C->mu_s[mu_s_panel_base(i >> 5) + (size_t)i * coop_mu_stride(*C, i >> 5) + (i & 31)] = C->v.mu[mu_off(i, i)];
   __syncwarp();
 }
 

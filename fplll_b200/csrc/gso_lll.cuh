@@ -83,7 +83,7 @@ B200_OPFN int warp_babai(const View &v, WarpSmem &s, int kappa, int sr_end, int 
         s.xs[k]        = 0.0;
         if (k >= sr_start)
           loop_needed |= (fabs(scale2(bm[q], de)) > eta);  // get_mu, gso_interface.h:694-701
-        new_max = max(new_max, de + fexponent(bm[q]));         // get_max_mu_exp, gso_interface.cpp:88-98
+        new_max = max(new_max, de + fexponent_fast(bm[q]));         // get_max_mu_exp, gso_interface.cpp:88-98
       }
     }
     if (!__any_sync(FULL, loop_needed))

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 #if B200_MU_CACHE
     C->mu_s = bm + 3 * (size_t)((S.d + 32 + 1) & ~1);
     C->mu_s_panels = mu_panels;
+    C->mu_last_p = n_panels(S.d) - 1, C->mu_last_stride = mu_s_last_stride(S.d);
 #endif
     C->cmd = COOP_EXIT, C->flag = 1;
   }
@@ -118,9 +119,19 @@ int b200gso_lll_cta_launch(b200gso *h, int mode, double delta, double eta, int k
     if (mu_smem_on)
     {
       // cache as many leading mu panels as fit into the 227 KB of the CTA
-      while (mu_panels < n_panels(S.d) && sm + mu_s_panel_base(mu_panels + 1) * sizeof(double) <= (size_t)227 * 1024)
+      // full panels take 32 (p+1) columns of 33 doubles; the last panel of the lattice only its real rows (gso_cta.cuh)
+      const int P = n_panels(S.d);
+      size_t used = 0;
+      while (mu_panels < P)
+      {
+        const size_t cols = 32 * (size_t)(mu_panels + 1);
+        const size_t need = cols * (mu_panels == P - 1 ? mu_s_last_stride(S.d) : MU_SS);
+        if (sm + (used + need) * sizeof(double) > (size_t)227 * 1024)
+          break;
+        used += need;
         mu_panels++;
-      sm += mu_s_panel_base(mu_panels) * sizeof(double);
+      }
+      sm += used * sizeof(double);
     }
 #else
 #define LLL_CTA_EXTRA_ARG

@@ -54,8 +54,9 @@ __device__ inline void lower_clean(const View &v, int idx, int lane)
   }
 }
 
-// FP_NR<double>::exponent, nr_FP_d.inl:44
-__device__ inline long fexponent(double x) { return (long)ilogb(x) + 1; }
+// FP_NR<double>::exponent, nr_FP_d.inl:44 (out of line: ilogb is a 30-instruction routine, and the callers on the hot
+// paths only need it for zeros, subnormals and non-finite values)
+static __device__ __noinline__ long fexponent(double x) { return (long)ilogb(x) + 1; }
 
 // ---- exact power-of-two arithmetic without the math library --------------------------------------------------------
 // ldexp / frexp / ilogb are 10-20 instruction library routines; on the one-lattice critical paths (Babai's rounding,
@@ -66,11 +67,12 @@ __device__ inline double pow2d(int e)  // 2^e, |e| <= 1022
 {
   return __longlong_as_double((long long)(e + 1023) << 52);
 }
+static __device__ __noinline__ double ldexp_slow(double x, long e) { return ldexp(x, (int)e); }
 __device__ inline double scale2(double x, long e)  // == ldexp(x, e)
 {
   if (e > -1000 && e < 1000)
     return __dmul_rn(x, pow2d((int)e));
-  return ldexp(x, (int)e);
+  return ldexp_slow(x, e);
 }
 // exponent of FP_NR<double>::exponent() for a NORMAL non-zero x (ilogb(x) + 1); callers handle 0 / subnormals
 __device__ inline int fexp_normal(double x) { return (int)((__double_as_longlong(x) >> 52) & 0x7ff) - 1022; }
@@ -79,6 +81,7 @@ __device__ inline bool is_normal_nz(double x)
   const int be = (int)((__double_as_longlong(x) >> 52) & 0x7ff);
   return be != 0 && be != 0x7ff;
 }
+__device__ inline long fexponent_fast(double x) { return is_normal_nz(x) ? (long)fexp_normal(x) : fexponent(x); }
 
 // FP_NR<double>::get_si_exp_we, nr_FP_d.inl:46-53
 __device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
@@ -87,13 +90,22 @@ __device__ inline long get_si_exp_we(double x, long &expo, long expo_add)
     expo = 0;
   else
   {
-    long e = (is_normal_nz(x) ? (long)fexp_normal(x) : fexponent(x)) + expo_add - 63;
+    long e = fexponent_fast(x) + expo_add - 63;
     expo   = e > 0 ? e : 0;
   }
   return (long)scale2(x, expo_add - expo);
 }
 
-// FP_NR<double>::rnd_we, nr_FP_d.inl:226-233 (rint = round-half-even)
+// FP_NR<double>::rnd_we, nr_FP_d.inl:226-233 (rint = round-half-even).  The library form lives out of line: inlined
+// into every unrolled step of the back-substitution it made those loops ~370 instructions per step, and a lone warp
+// streaming 200 KB of straight-line code through the instruction caches per call was what the single-lattice LLL spent
+// most of its time on (profiles/r2_lll_phase_breakdown.txt: 1100 cycles per row before, the arithmetic needs ~80).
+static __device__ __noinline__ double rnd_we_slow(double x, long expo_add)
+{
+  if (fexponent(x) + expo_add >= 53)
+    return x;
+  return ldexp(rint(ldexp(x, (int)expo_add)), (int)-expo_add);
+}
 __device__ inline double rnd_we(double x, long expo_add)
 {
   if (expo_add == 0 && fabs(x) < 4503599627370496.0)  // |x| < 2^52: both branches below reduce to rint(x)
@@ -106,9 +118,7 @@ __device__ inline double rnd_we(double x, long expo_add)
     // an integer times 2^-e is exact
     return __dmul_rn(rint(__dmul_rn(x, pow2d((int)expo_add))), pow2d((int)-expo_add));
   }
-  if (fexponent(x) + expo_add >= 53)
-    return x;
-  return ldexp(rint(ldexp(x, (int)expo_add)), (int)-expo_add);
+  return rnd_we_slow(x, expo_add);
 }
 
 // One thread's ordered chain  a = a (+|-) x[0] (+|-) x[1] ... over n shared-memory values, optionally recording every
