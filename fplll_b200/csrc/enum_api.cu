@@ -717,8 +717,10 @@ const Tuning &tuning()
     q.use_xs         = (int)geti("B200_ENUM_XS", 1);
     q.xs_threads_cap = (int)geti("B200_ENUM_XS_THREADS", 320);
     // hand-off threshold: a call that has visited this many nodes on the first device and still has work pending is
-    // spread over all devices (4 M nodes = ~0.5 ms of one B200; the hand-off itself costs ~0.1 ms)
-    q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 4000000);
+    // spread over all devices.  32 M nodes = ~4 ms of one B200 against ~0.5 ms for the hand-off (peer copies, one
+    // cooperative launch and one read-back per device): of the ~18 k enumerations of a BKZ-60 tour on dim 200 only a
+    // handful ever get there, so a tour never pays for devices it cannot use.
+    q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 32000000);
     q.min_roots   = (int)geti("B200_ENUM_MIN_ROOTS", MIN_ROOTS);
     // rounds with fewer tasks than warps are bound by the latency of a lone walker (~0.35 us per node): yield sooner
     q.yield_small = (unsigned)geti("B200_ENUM_YIELD_SMALL", 8);  // BKZ-60 tour: 4.9 s -> 3.5 s of enumeration (gpurun_out/r2)

@@ -105,7 +105,7 @@ def test_two_devices_in_one_process_visit_the_same_nodes(en):
     from fplll_b200._lib import load
     if load("libb200enum.so").b200enum_device_count() < 2:
         pytest.skip("one GPU visible (the driver's round-end run has one; gpurun --gpus 2 runs this)")
-    # a call this small stays on the first device (hand-off threshold B200_ENUM_FAN_NODES, 4 M nodes) ...
+    # a call this small stays on the first device (hand-off threshold B200_ENUM_FAN_NODES, 32 M nodes) ...
     z = H.gold("enum_r200_b30_unpruned.npz")
     R = 0.55 * float(z["maxdist"])
     ref = O.enum_svp(z["mut"], z["rdiag"], None, R, shrink=False)

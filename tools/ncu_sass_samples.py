@@ -6,6 +6,7 @@ import sys
 rows = list(csv.reader(sys.stdin))
 hdr = None
 out = []
+base = None
 for r in rows:
     if hdr is None:
         if "Address" in r:
@@ -14,6 +15,8 @@ for r in rows:
     if len(r) != len(hdr):
         continue
     d = dict(zip(hdr, r))
+    if base is None:
+        base = d.get("Address")
     samp = None
     for k in ("Warp Stall Sampling (All Samples)", "# Samples", "Sampling Data (All)"):
         if k in d:
@@ -28,6 +31,7 @@ for r in rows:
     stalls = {k: d[k] for k in d if k.startswith("stall_") and d[k] not in ("0", "", "0.0")}
     out.append((sv, d.get("Address", "?"), d.get("Source", "")[:60], d.get("Instructions Executed", ""), stalls))
 print("columns:", hdr)
+print("kernel base address:", base)
 print("sampled instructions:", len(out), "total samples:", sum(o[0] for o in out))
 for sv, addr, src, ex, st in sorted(out, reverse=True)[:400]:
     print("%8.0f %s exec=%s | %s | %s" % (sv, addr, ex, src, " ".join("%s=%s" % (k.replace("stall_", ""), v) for k, v in st.items())))
