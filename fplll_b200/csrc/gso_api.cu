@@ -6,7 +6,7 @@
 // sweep loops) is what hides DRAM latency, not shared-memory tiling.  There is no CPU fallback anywhere.
 #include "gso_common.cuh"
 #include "gso_gram.cuh"
-#include "gso_tma.cuh"
+#include "gso_stream.cuh"
 
 thread_local std::string b200gso_g_err;
 long b200gso_g_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -99,39 +99,12 @@ __global__ void k_discover_all(Batch S, int upto)
     warp_discover_row(v, lane);
 }
 
-// TMA-staged variant (gso_tma.cuh): per warp  vb | rrow | murow | ring[TMA_STAGES][512] | mbarriers
-__host__ __device__ inline size_t tma_warp_doubles(int d, int n)
+// TMA-fed streaming variant (gso_stream.cuh): one persistent CTA per SM, every warp walks its own lattices
+__global__ void __launch_bounds__(ST_MAX_CONS * 32, 1)
+    k_update_row_stream(const __grid_constant__ Batch S, int i, int last_j, int *ok, const __grid_constant__ StreamMaps M)
 {
-  return ((WarpSmem::doubles(d, n, false) + 15) & ~(size_t)15) + (size_t)TMA_STAGES * TMA_CHUNK_DBL + TMA_STAGES;
-}
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) k_update_row_tma(Batch S, int i, int last_j, int *ok)
-{
-  extern __shared__ __align__(128) double smem_t[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int l = blockIdx.x * (blockDim.x >> 5) + w;
-  if (l >= S.B)
-    return;
-  double *base = smem_t + (size_t)w * tma_warp_doubles(S.d, S.n);
-  WarpSmem s;
-  s.carve(base, S.d, S.n, false);
-  double *ring = base + ((WarpSmem::doubles(S.d, S.n, false) + 15) & ~(size_t)15);
-  unsigned long long *bars = (unsigned long long *)(ring + (size_t)TMA_STAGES * TMA_CHUNK_DBL);
-  View v = S.view(l);
-  if (i >= v.meta[M_NKR])
-    warp_discover_row(v, lane);
-  // fast path only for a full recompute: nothing of row i valid, whole Gram row invalid
-  int notnan = 0;
-  const double *gfrow = v.gf + tri_off(i);
-  for (int j = lane; j <= last_j; j += 32)
-    notnan |= (gfrow[j] == gfrow[j]);
-  notnan = __any_sync(FULL, notnan);
-  bool r;
-  if (v.valid[i] <= 0 && !notnan)
-    r = warp_update_gso_row_tma(v, i, last_j, s, ring, bars, lane);
-  else
-    r = warp_update_gso_row(v, i, last_j, s, lane);
-  if (ok && lane == 0)
-    ok[l] = r ? 1 : 0;
+  extern __shared__ __align__(128) double smem_st[];
+  stream_update_rows(S, M, i, last_j, ok, smem_st);
 }
 
 template <int MINB>
@@ -415,23 +388,115 @@ static int upd_variant()
   }
   return v;
 }
-static void launch_update_row(b200gso *h, int i, int last_j);
+// ---- tensor maps of the streaming kernel (driver entry point resolved at run time: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  static bool tried       = false;
+  if (!tried)
+  {
+    tried   = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static bool encode_f64(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                       const cuuint32_t *box, int l2promo)
+{
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn)
+    return false;
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapL2promotion pr = l2promo == 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                    : l2promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                    : l2promo == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                     : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// full-panel maps once per handle, the partial-panel maps whenever the row count of the last panel changes
+static bool stream_maps(b200gso *h, int rows_last)
+{
+  const Batch &S = h->S;
+  static const int promo = getenv("B200_ST_L2PROMO") ? atoi(getenv("B200_ST_L2PROMO")) : 256;
+  const cuuint64_t bf_dims[3] = {32, (cuuint64_t)S.n, (cuuint64_t)S.B * n_panels(S.d)};
+  const cuuint64_t bf_str[2]  = {256, (cuuint64_t)256 * S.n};
+  const cuuint64_t mu_dims[3] = {32, (cuuint64_t)S.B * (S.mu_stride / 32), 1};
+  const cuuint64_t mu_str[2]  = {256, (cuuint64_t)256 * S.B * (S.mu_stride / 32)};
+  CUtensorMap *m = h->st_maps.m;
+  if (h->st_state == 0)
+  {
+    const cuuint32_t bx[3] = {32, ST_COLS, 1}, bb[3] = {16, 16, 1};
+    const bool okm = encode_f64(&m[SM_BF_FULL], S.bf, 3, bf_dims, bf_str, bx, promo) &&
+                     encode_f64(&m[SM_MU_FULL], S.mu, 3, mu_dims, mu_str, bx, promo) &&
+                     encode_f64(&m[SM_MU_B], S.mu, 3, mu_dims, mu_str, bb, 128);
+    h->st_state    = okm ? 1 : -1;
+    h->st_rows     = 0;
+  }
+  if (h->st_state < 0)
+    return false;
+  if (rows_last < 32 && rows_last != h->st_rows)
+  {
+    const cuuint32_t bx[3] = {(cuuint32_t)rows_last, ST_COLS, 1};
+    const int pp           = rows_last * 8 >= 256 ? 256 : rows_last * 8 >= 128 ? 128 : rows_last * 8 >= 64 ? 64 : 0;
+    if (!encode_f64(&m[SM_BF_PART], S.bf, 3, bf_dims, bf_str, bx, pp) ||
+        !encode_f64(&m[SM_MU_PART], S.mu, 3, mu_dims, mu_str, bx, pp))
+    {
+      h->st_state = -1;
+      return false;
+    }
+    h->st_rows = rows_last;
+  }
+  else if (h->st_rows == 0)
+  {
+    // never used by a launch without a partial panel, but the parameter block must hold valid descriptors
+    m[SM_BF_PART] = m[SM_BF_FULL];
+    m[SM_MU_PART] = m[SM_MU_FULL];
+    h->st_rows    = 32;
+  }
+  return true;
+}
 
 static void launch_update_row(b200gso *h, int i, int last_j)
 {
   const int g = grid_warps(h), t = WARPS_PER_CTA * 32;
-  static const int use_tma = getenv("B200_UPD_TMA") ? atoi(getenv("B200_UPD_TMA")) : 0;
-  if (use_tma)
+  // B200_UPD_STREAM=0: the register-staged kernel (k_update_row) for every launch
+  // (read per call: the parity tests switch kernels inside one process)
+  const char *us_      = getenv("B200_UPD_STREAM");
+  const int use_stream = us_ ? atoi(us_) : 0;
+  if (use_stream && !h->S.host_basis)
   {
-    const size_t sm = (size_t)WARPS_PER_CTA * tma_warp_doubles(h->S.d, h->S.n) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set)
+    // consumer warps per CTA: as many as the shared memory holds (<= ST_MAX_CONS), preferring a count that deals the
+    // batch evenly over the SMs x NW warps (a warp with one lattice more than the others is the tail of the launch)
+    static const int wmax = getenv("B200_ST_WARPS") ? std::max(1, std::min(ST_MAX_CONS, atoi(getenv("B200_ST_WARPS")))) : ST_MAX_CONS;
+    const size_t per = stream_warp_doubles(h->S.d, h->S.n) * sizeof(double);
+    const StreamShape sh = stream_shape(i, last_j);
+    const int NC         = stream_num_chunks(sh, h->S.n);
+    const size_t tabb    = (size_t)NC * sizeof(StreamDesc);
+    const int cap = tabb + per > (size_t)SMEM_OPTIN_MAX ? 0 : (int)std::min<size_t>(wmax, ((size_t)SMEM_OPTIN_MAX - tabb) / per);
+    int NW = 0;
+    double best = 0;
+    for (int w = std::max(1, cap / 2); w <= cap && cap > 0; w++)
     {
-      cudaFuncSetAttribute((const void *)k_update_row_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
+      const long slots = (long)h->sm_count * w, rounds = (h->S.B + slots - 1) / slots;
+      const double eff = (double)h->S.B / (double)(slots * rounds);
+      if (eff >= best - 1e-12)
+        best = eff, NW = w;
     }
-    k_update_row_tma<<<g, t, sm, h->stream>>>(h->S, i, last_j, h->d_ok);
-    return;
+    // (a row with fewer chunks than ring stages, i <= 1 or so, is not worth a stream: the register kernel takes it)
+    if (NW >= 1 && NC >= ST_STAGES && (size_t)h->S.ldb * 8 <= ST_STAGE_DBL * sizeof(double) && stream_maps(h, sh.rows_last))
+    {
+      const int ctas = std::min(h->sm_count, (h->S.B + NW - 1) / NW);
+      k_update_row_stream<<<ctas, NW * 32, NW * per + tabb, h->stream>>>(h->S, i, last_j, h->d_ok, h->st_maps);
+      return;
+    }
   }
   switch (upd_variant())  // unknown values take <5>, here and in b200gso_resident_lattices
   {
@@ -493,6 +558,7 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
   }
   b200gso *h = new b200gso();
   h->device  = device;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   Batch &S   = h->S;
   S.B = batch, S.d = d, S.n = n, S.ldb = ld_b(n), S.row_expo_en = (flags & B200GSO_ROW_EXPO) ? 1 : 0;
   S.host_basis = (flags & B200GSO_HOST_BASIS) ? 1 : 0;
@@ -556,6 +622,7 @@ int b200gso_create(b200gso_t **out, int batch, int d, int n, int flags, int devi
     return B200GSO_EINVAL;
   }
   const void *fns[] = {(const void *)k_init,         (const void *)k_discover_all, (const void *)k_update_row<8>, (const void *)k_update_row<6>, (const void *)k_update_row<5>,
+                       (const void *)k_update_row_stream,
                        (const void *)k_update_gso,   (const void *)k_row_addmul_we, (const void *)k_row_op_end,
                        (const void *)k_row_swap,     (const void *)k_move_row,     (const void *)k_upload_row,
                        (const void *)k_apply_ops,    (const void *)k_upload_row_fp, (const void *)k_init_host_basis};

@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/b200gso.h"
 #include "gso_lll.cuh"
+#include "gso_stream.cuh"
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
@@ -130,6 +131,10 @@ struct b200gso
   b200gso_op *h_ops;
   size_t h_ops_cap;
   std::vector<void *> allocs;
+  // streaming update kernel (gso_stream.cuh): tensor maps (0 = not built yet, 1 = ready, -1 = unavailable), the row
+  // count the partial-panel maps were encoded for, SMs of the device
+  StreamMaps st_maps;
+  int st_state = 0, st_rows = 0, sm_count = 0;
 };
 
 inline int grid_warps(const b200gso *h) { return (h->S.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }

@@ -382,3 +382,51 @@ def test_two_live_handles_of_different_size(fb):
     mo = O.OracleGSO(big[0])
     assert mo.lll(0.99, 0.51)["status"] == 0
     assert np.array_equal(mb.b[0], mo.state()["b"])
+
+
+@pytest.mark.parametrize("d,n,B,bits", [(70, 75, 1600, 20), (200, 201, 800, 20), (96, 96, 777, 30)])
+def test_streaming_update_row_equals_register_kernel_and_oracle(fb, monkeypatch, d, n, B, bits):
+    """The three batched update_gso_row kernels on the same states, bit for bit, and against the oracle on a sample of
+    lattices: the register-staged kernel (the default) and the TMA-fed streaming kernel (B200_UPD_STREAM=1,
+    gso_stream.cuh).  The batch is larger than the
+    streaming kernel's resident warps so every warp streams across lattice boundaries, and the lattices are in mixed
+    states: full recompute, Gram row partly valid, row already valid, partial update (last_j < i)."""
+    rng = np.random.default_rng(d)
+    base = rng.integers(-(1 << bits), 1 << bits, size=(8, d, n), dtype=np.int64)
+    b = base[rng.integers(0, 8, size=B)]
+    x = rng.integers(-3, 4, size=B).astype(np.float64)
+    rows = [d - 1, 33, 1, 0, d - 9, 64 if d > 64 else 31]
+    states = {}
+    for stream in ("1", "0"):
+        monkeypatch.setenv("B200_UPD_STREAM", stream)
+        m = fb.MatGSO(b)
+        assert m.update_gso().all()
+        out = []
+        for i in rows:
+            if i:
+                m.row_addmul_we(i, i - 1, x, 0)                  # some lattices get x = 0: still a row_op_end
+            m.row_op_end(i, i + 1)
+            if i > 40:
+                assert m.update_gso_row(i, i - 7).all()          # partial row first, then the rest of it
+            assert m.update_gso_row(i, i).all()
+            if i + 1 < d:
+                assert m.update_gso_row(i + 1, i + 1).all()      # row i + 1: only its Gram entry (i+1, i) is invalid
+        states[stream] = m.state()
+        m.close()
+    a, c = states["1"], states["0"]
+    for k in ("mu", "r", "gf", "bf"):
+        assert H.eq_f64(a[k], c[k]), k
+    assert np.array_equal(a["gso_valid_cols"], c["gso_valid_cols"])
+    for l in (0, 1, B // 2, B - 1):
+        mo = O.OracleGSO(b[l])
+        mo.update_gso()
+        for i in rows:
+            if i:
+                mo.row_addmul_we(i, i - 1, x[l], 0)
+            mo.row_op_end(i, i + 1)
+            if i > 40:
+                mo.update_gso_row(i, i - 7)
+            mo.update_gso_row(i, i)
+            if i + 1 < d:
+                mo.update_gso_row(i + 1, i + 1)
+        H.assert_state_equal(H.lattice_state(a, l), mo.state(), "lattice %d" % l)
