@@ -202,7 +202,7 @@ def hh_extras(local):
         T = i * n - i * (i - 1) // 2
         per = 8 * (T + 2 * n)
         peak, _ = peaks()
-        out_variant = "hk_update_R"
+        out_variant = "hk_update_R_x32" if os.environ.get("B200_HH_X32") == "1" else "hk_update_R"
         out = {"workload": "batched update_R(399, false) on %d lattices of d=n=400 (V = the reflections of rows 0..398)" % B,
                "kernel": out_variant,
                "algorithmic_bytes_per_lattice": per, "ms_per_launch": ms, "GBps": B * per / (ms * 1e-3) / 1e9,

@@ -948,8 +948,18 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
 
   // ---- phase A: the first device ----
   CKE(cudaSetDevice(home->device));
-  CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, up_end - DevCtx::OFF_WORDS,
-                      cudaMemcpyHostToDevice, home->stream));
+  if (ipc)
+  {
+    // every word but the shared ticket: a peer that starts this call earlier may already be claiming from it (its owner
+    // never resets it — k_epoch below installs the call's epoch on whichever rank gets there first)
+    const size_t tk = DevCtx::OFF_WORDS + (size_t)W_GTICKET * 8;
+    CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, tk - DevCtx::OFF_WORDS,
+                        cudaMemcpyHostToDevice, home->stream));
+    CKE(cudaMemcpyAsync(home->d_blk + tk + 8, home->h_up + tk + 8, up_end - tk - 8, cudaMemcpyHostToDevice, home->stream));
+  }
+  else
+    CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, up_end - DevCtx::OFF_WORDS,
+                        cudaMemcpyHostToDevice, home->stream));
   CKE(cudaEventRecord(home->e0, home->stream));
   EnumArgs a0;
   make_args(home, a0);

@@ -12,7 +12,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math_constants.h>
 #include <string>
 #include <vector>
@@ -721,6 +723,232 @@ __global__ void hk_set_updated(HBatch S, int val)
 
 }  // namespace
 
+// =====================================================================================================================
+// update_R with 32 lattices per warp: lane = lattice (batched calls, history off).
+//
+// hk_update_R (one warp per lattice) forms every dot product V_j . R_i as per-lane products followed by ONE lane adding
+// them in the reference's order: that single-lane chain takes a full warp issue slot per add and the kernel is issue-bound
+// at 0.19 of the HBM peak (profiles/r1_enum_hh_ncu_summary.txt).  With one LATTICE per lane the 32 chains of a group of
+// lattices advance in one instruction.  The state stays row-major per lattice (hview): the transposition is done by the
+// TMA unit — a tensor map over V (and R) seen as {flat d*n elements} x {lattice} delivers boxes of 16 consecutive elements
+// x 32 lattices (128-byte segments of 32 different rows of HBM) into shared memory with the 128-byte swizzle, which lane r
+// reads back as 8 conflict-free LDS.128 of its own row.  R_i of the 32 lattices lives in shared memory as [k][lane].
+// Reflection j's update  R[k] += V_j[k] * f_j  and reflection j+1's dot product  sum_k V_{j+1}[k] * R[k]  run fused in one
+// sweep over k (the dot product of j+1 only needs R[k] after the update of j at the same k), so V is streamed once from
+// HBM and once more from L2, and every element costs one dependent DADD (8 cycles) instead of two passes.
+// Operation order per lattice is exactly w_update_R's (householder.cpp:151-184): bit-identical R.
+constexpr int X_STAGES  = 8;
+constexpr int X_K       = 16;                 // elements of a row per chunk
+constexpr int X_HALF_DBL = 32 * X_K;          // one box: 32 lattices x 16 doubles (4 KB)
+constexpr int X_STAGE_DBL = 2 * X_HALF_DBL;   // A (V_j) + B (V_{j+1})
+
+struct XMaps
+{
+  CUtensorMap V, R;  // {d*n, B}, box {16, 32}, SWIZZLE_128B
+};
+
+__device__ inline unsigned x_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ inline void x_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile("{\n\t"
+               ".reg .pred p;\n\t"
+               "XW_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra XD_%=;\n\t"
+               "bra XW_%=;\n\t"
+               "XD_%=:\n\t"
+               "}" ::"r"(x_smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+__device__ inline void x_tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                   "r"(x_smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(x_smem_u32(bar))
+               : "memory");
+}
+
+// the chunk sequence: pass -2 loads R_i; pass j = -1 .. i-1 sweeps k from (max(j,0) & ~15) to n in steps of 16 with
+// A = V_j (j >= 0) and B = V_{j+1} (j + 1 < i)
+struct XIter
+{
+  int j, k0;
+  __device__ void start() { j = -2, k0 = 0; }
+  __device__ bool done(int i) const { return j >= i; }
+  __device__ void next(int n, int i)
+  {
+    k0 += X_K;
+    if (k0 >= n)
+    {
+      j++;
+      if (j == -1 && i < 1)
+        j = 0;  // no reflections at all: nothing after the load
+      k0 = max(j, 0) & ~(X_K - 1);
+    }
+  }
+};
+
+// lane r's 16 elements of a swizzled box: element k at row r, 16-byte column (k >> 1) ^ (r & 7)
+__device__ inline void x_read_box(const double *box, int lane, double (&v)[X_K])
+{
+  const char *row = (const char *)box + lane * 128;
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+  {
+    const double2 t = *(const double2 *)(row + ((c ^ (lane & 7)) << 4));
+    v[2 * c] = t.x, v[2 * c + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(32, 1) hk_update_R_x32(HBatch S, int i, const __grid_constant__ XMaps M)
+{
+  extern __shared__ unsigned char x_raw[];
+  const int lane = threadIdx.x, n = S.n;
+  const int l0 = blockIdx.x * 32, l = l0 + lane;
+  double *ring = (double *)(((size_t)x_raw + 1023) & ~(size_t)1023);
+  double *Rk   = ring + (size_t)X_STAGES * X_STAGE_DBL;  // [k][lane]
+  const int npad = (n + X_K - 1) & ~(X_K - 1);
+  unsigned long long *bars = (unsigned long long *)(Rk + (size_t)npad * 32);
+  if (lane == 0)
+  {
+    for (int q = 0; q < X_STAGES; q++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(bars + q)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  const bool live = l < S.B && !S.meta[(size_t)min(l, S.B - 1) * HM_STRIDE + HM_UPDATED];
+  const size_t dn = (size_t)S.d * n;
+
+  XIter prod, cons;
+  prod.start(), cons.start();
+  unsigned issued = 0, consumed = 0;
+  auto issue = [&]() {
+    if (prod.done(i))
+      return;
+    if (lane == 0)
+    {
+      double *dst             = ring + (size_t)(issued % X_STAGES) * X_STAGE_DBL;
+      unsigned long long *bar = bars + (issued % X_STAGES);
+      if (prod.j == -2)
+      {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)), "r"(X_HALF_DBL * 8) : "memory");
+        x_tma_2d(dst, &M.R, i * n + prod.k0, l0, bar);
+      }
+      else
+      {
+        const bool hasA = prod.j >= 0, hasB = prod.j + 1 < i;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)),
+                     "r"((int)(hasA + hasB) * X_HALF_DBL * 8)
+                     : "memory");
+        if (hasA)
+          x_tma_2d(dst, &M.V, prod.j * n + prod.k0, l0, bar);
+        if (hasB)
+          x_tma_2d(dst + X_HALF_DBL, &M.V, (prod.j + 1) * n + prod.k0, l0, bar);
+      }
+    }
+    issued++;
+    prod.next(n, i);
+  };
+  for (int q = 0; q < X_STAGES; q++)
+    issue();
+
+  double acc = 0.0, f0 = 0.0, sg = 1.0, sg_next = 1.0;
+  // sigma of reflection 0 (householder.cpp:176: R(i,j) *= sigma[j])
+  if (i > 0)
+    sg_next = S.sigma[(size_t)min(l, S.B - 1) * S.d];
+  while (!cons.done(i))
+  {
+    const int j = cons.j, k0 = cons.k0;
+    x_mbar_wait(bars + (consumed % X_STAGES), (consumed / X_STAGES) & 1u);
+    const double *st = ring + (size_t)(consumed % X_STAGES) * X_STAGE_DBL;
+    if (j == -2)
+    {
+      double a[X_K];
+      x_read_box(st, lane, a);
+#pragma unroll
+      for (int u = 0; u < X_K; u++)
+        Rk[(size_t)(k0 + u) * 32 + lane] = a[u];
+    }
+    else
+    {
+      const bool hasA = j >= 0, hasB = j + 1 < i;
+      if (k0 == (max(j, 0) & ~(X_K - 1)))
+      {
+        // first chunk of the pass: the factor of reflection j is the dot product the previous pass accumulated
+        f0 = -acc;
+        sg = sg_next;
+        if (j + 1 < i)
+          sg_next = S.sigma[(size_t)min(l, S.B - 1) * S.d + j + 1];
+      }
+      double a[X_K], b[X_K];
+      if (hasA)
+        x_read_box(st, lane, a);
+      if (hasB)
+        x_read_box(st + X_HALF_DBL, lane, b);
+      double *rp = Rk + (size_t)k0 * 32 + lane;
+      if (k0 > j + 1 && k0 + X_K <= n && hasA && hasB)
+      {
+        // interior chunk: every element takes the update of j and a term of the chain of j + 1
+        double r[X_K];
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          r[u] = __dadd_rn(rp[u * 32], __dmul_rn(a[u], f0));
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          rp[u * 32] = r[u];
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          r[u] = __dmul_rn(b[u], r[u]);
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          acc = __dadd_rn(acc, r[u]);
+      }
+      else
+      {
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+        {
+          const int k = k0 + u;
+          double r    = rp[u * 32];
+          if (hasA && k >= j && k < n)
+          {
+            r = __dadd_rn(r, __dmul_rn(a[u], f0));
+            if (k == j)
+              r = __dmul_rn(sg, r);
+            rp[u * 32] = r;
+          }
+          if (hasB && k >= j + 1 && k < n)
+          {
+            const double t = __dmul_rn(b[u], r);
+            acc            = (k == j + 1) ? t : __dadd_rn(acc, t);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    consumed++;
+    issue();
+    cons.next(n, i);
+  }
+  if (live)
+  {
+    double *Rr = S.R + (size_t)l * dn + (size_t)i * n;
+    for (int k = 0; k < n; k++)
+      Rr[k] = Rk[(size_t)k * 32 + lane];
+  }
+}
+
+__global__ void hk_update_R_last_cond(HBatch S, int i)
+{
+  HView v;
+  double *sR, *sP;
+  int lane;
+  if (hsetup(S, v, sR, sP, lane) && !v.meta[HM_UPDATED])
+    w_update_R_last(v, i, sP, lane);
+}
+
 struct b200hh
 {
   HBatch S;
@@ -731,6 +959,8 @@ struct b200hh
   double *d_hlll = nullptr;  // dR, eR, prevR: 3 x B x d
   int *d_hlll_i = nullptr;   // prevE: B x d, status: B
   unsigned long long *d_hlll_it = nullptr;
+  XMaps xmaps;
+  int x_state = 0;  // tensor maps of hk_update_R_x32: 0 not built, 1 ready, -1 unavailable
   std::vector<void *> allocs;
 };
 
@@ -748,6 +978,56 @@ template <class T> static int hh_alloc(b200hh *h, T **p, size_t count)
   return 0;
 }
 static int hgrid(const b200hh *h) { return (h->S.B + HW - 1) / HW; }
+
+// tensor maps of the lane-per-lattice kernel (driver entry point resolved at run time: no link-time libcuda dependency)
+static bool x_maps(b200hh *h)
+{
+  if (h->x_state)
+    return h->x_state > 0;
+  h->x_state = -1;
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return false;
+  const HBatch &S = h->S;
+  const size_t dn = (size_t)S.d * S.n;
+  if (dn % 2)
+    return false;  // lattice stride must be a multiple of 16 bytes
+  const cuuint64_t dims[2] = {(cuuint64_t)dn, (cuuint64_t)S.B}, str[1] = {(cuuint64_t)dn * 8};
+  const cuuint32_t box[2] = {X_K, 32}, es[2] = {1, 1};
+  for (int w = 0; w < 2; w++)
+    if (((EncodeFn)p)(w ? &h->xmaps.R : &h->xmaps.V, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, w ? (void *)S.R : (void *)S.V, dims, str,
+                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  h->x_state = 1;
+  return true;
+}
+
+static void launch_update_R_h(b200hh *h, int i, int last_j)
+{
+  const HBatch &S = h->S;
+  // B200_HH_X32=1 selects the lane-per-lattice kernel (default: one warp per lattice).  It needs a batch (32 lattices per
+  // warp), no R_history (its scattered per-lattice writes would cost more than the V stream) and R_i of 32 lattices in
+  // shared memory — which caps it at ONE warp per SM at n = 400, and one warp issues an instruction every ~3.7 cycles:
+  // measured 0.171 of the HBM peak against 0.181 for hk_update_R on 4736 lattices (profiles/r2_hh_x32.txt), so it is
+  // kept as the tested starting point of the multi-warp form, not as the default.
+  const char *e     = getenv("B200_HH_X32");
+  const int use_x32 = e ? atoi(e) : 0;
+  const size_t npad = ((size_t)S.n + X_K - 1) & ~(size_t)(X_K - 1);
+  const size_t smx  = 1024 + (size_t)X_STAGES * X_STAGE_DBL * 8 + npad * 32 * 8 + X_STAGES * 8;
+  if (use_x32 && S.B >= 64 && !S.keep_hist && i > 0 && smx <= 227 * 1024 && (size_t)S.d * S.n < (1ull << 31) && x_maps(h))
+  {
+    hk_update_R_x32<<<(S.B + 31) / 32, 32, smx, h->stream>>>(S, i, h->xmaps);
+    if (last_j)
+      hk_update_R_last_cond<<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, i);
+    return;
+  }
+  launch_update_R(S, hgrid(h), h->smem, h->stream, i, last_j);
+}
 
 extern "C" {
 
@@ -799,6 +1079,7 @@ int b200hh_create(b200hh_t **out, int batch, int d, int n, int flags, int device
   const void *fns[] = {(const void *)hk_init,        (const void *)hk_refresh_R_bf, (const void *)hk_refresh_R,
                        (const void *)hk_update_R<4>, (const void *)hk_update_R<8>, (const void *)hk_update_R<14>,
                        (const void *)hk_update_R<32>, (const void *)hk_update_R_last, (const void *)hk_size_reduce,
+                       (const void *)hk_update_R_x32, (const void *)hk_update_R_last_cond,
                        (const void *)hk_swap,        (const void *)hk_recover_R,   (const void *)hk_hlll<4>,
                        (const void *)hk_hlll<8>,     (const void *)hk_hlll<14>,     (const void *)hk_hlll<32>};
   for (const void *f : fns)
@@ -878,7 +1159,7 @@ int b200hh_refresh_R(b200hh_t *h, int i)
 }
 int b200hh_update_R(b200hh_t *h, int i, int last_j)
 {
-  HH_CALL(i >= 0 && i < h->S.d && h->S.n <= 32 * 31, launch_update_R(h->S, hgrid(h), h->smem, h->stream, i, last_j))
+  HH_CALL(i >= 0 && i < h->S.d && h->S.n <= 32 * 31, launch_update_R_h(h, i, last_j))
 }
 int b200hh_update_R_last(b200hh_t *h, int i)
 {
@@ -967,7 +1248,7 @@ int b200hh_time_update_R(b200hh_t *h, int i, int reps, float *ms_update_mean)
   {
     hk_refresh_R<<<hgrid(h), HW * 32, h->smem, h->stream>>>(h->S, i);
     CKH(cudaEventRecord(ev[2 * r], h->stream));
-    launch_update_R(h->S, hgrid(h), h->smem, h->stream, i, 0);
+    launch_update_R_h(h, i, 0);
     CKH(cudaEventRecord(ev[2 * r + 1], h->stream));
   }
   CKH(cudaStreamSynchronize(h->stream));

@@ -136,3 +136,35 @@ def test_hlll_config3_sublattice_of_q400(fb=None):
     out, st = fplll_b200.hlll_reduction(z["q400sub_in"].copy())
     assert st == int(z["q400sub_status"]) == 0
     assert np.array_equal(out, z["q400sub_out"])
+
+
+@pytest.mark.parametrize("d,n,B,bits", [(40, 40, 70, 20), (33, 50, 97, 12), (64, 64, 64, 30)])
+def test_update_R_lane_per_lattice_equals_warp_per_lattice_and_oracle(monkeypatch, d, n, B, bits):
+    """hk_update_R_x32 (32 lattices per warp, operands transposed by the TMA unit; taken for batches without R_history)
+    against hk_update_R (one warp per lattice, B200_HH_X32=0) on the same QR sweep, bit for bit, and against the oracle
+    on a sample of lattices.  Batches that are not a multiple of 32, n not a multiple of 16, d < n."""
+    from fplll_b200.householder import MatHouseholder
+    rng = np.random.default_rng(1000 + d)
+    b = rng.integers(-(1 << bits), 1 << bits, size=(B, d, n), dtype=np.int64)
+    states = {}
+    for x32 in ("1", "0"):
+        monkeypatch.setenv("B200_HH_X32", x32)
+        m = MatHouseholder(b, 5, keep_history=False)
+        for i in range(d):
+            m.refresh_R_bf(i)
+            m.update_R(i, last_j=(i % 3 != 1))   # both forms of the call: with and without update_R_last
+            if i % 3 == 1:
+                m.update_R_last(i)
+        states[x32] = m.state()
+        m.close()
+    a, c = states["1"], states["0"]
+    for k in ("R", "V", "sigma"):
+        assert H.eq_f64(a[k], c[k]), k
+    for l in (0, 31, 32, B - 1):
+        mo = O.OracleHouseholder(b[l], 5)
+        for i in range(d):
+            mo.refresh_R_bf(i)
+            mo.update_R(i)
+        s = mo.state()
+        assert H.eq_f64(a["R"][l], s["R"]), "R lattice %d" % l
+        assert H.eq_f64(a["V"][l], s["V"]), "V lattice %d" % l
