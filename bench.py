@@ -269,10 +269,11 @@ def bkz_extras(local, devices=None, with_ref=True):
         # fp64 BKZ on this basis is fragile in the reference itself: its own bkz_reduction dies with "infinite loop in
         # babai" (RedStatus 3) for 2 of 5 RNG seeds within one tour (measured with oracle/_ref), so a
         # failed attempt is retried with the next rerandomisation seed, every attempt is reported
-        # (seed 2 first: on ONE device seed 1 ends in RED_BABAI_FAILURE near the end of the tour, on two devices it does not —
-        # profiles/r2_bkz60_runs.txt lists every run of this round)
+        # Every SVP call enumerates the fixed region of its initial radius (include/b200bkz.h: the default), so a tour is a
+        # function of (basis, seed) alone: seeds 1 and 3 end with status 8, seed 2 in RED_BABAI_FAILURE near the end of the
+        # tour — every time, on any number of devices (profiles/r2_bkz60_runs.txt).
         attempts = []
-        for seed in (2, 1, 3):
+        for seed in (1, 3, 2):
             b = g["b"].copy()
             t0 = time.perf_counter()
             st, stats = fb.bkz_reduction(b, fb.BKZParam(60, strategies="default",

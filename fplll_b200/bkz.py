@@ -9,6 +9,7 @@ from ._lib import B200Error, load
 
 BKZ_DEFAULT, BKZ_VERBOSE, BKZ_NO_LLL, BKZ_MAX_LOOPS, BKZ_MAX_TIME = 0, 1, 2, 4, 8  # defs.h:264-274
 BKZ_BOUNDED_LLL, BKZ_AUTO_ABORT, BKZ_GH_BND = 0x10, 0x20, 0x80
+BKZ_SHRINK_RADIUS = 0x10000  # include/b200bkz.h: not a reference flag (order-dependent enumeration like the reference's)
 RED_BKZ_FAILURE, RED_BKZ_TIME_LIMIT, RED_BKZ_LOOPS_LIMIT = 6, 7, 8
 _P = C.POINTER
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "strategies_default.npz")

@@ -80,7 +80,11 @@ public:
       : ctx(ctx), g(g), d(d), top(top), st(st), rng(top.seed ? top.seed : 0x9e3779b97f4a7c15ull)
   {
     lll_delta = top.delta < 1 ? top.delta : 0.99;  // bkz.cpp:862
+    const char *e = getenv("B200_BKZ_SHRINK");      // experiment knob: 1 forces the shrinking radius, 0 the fixed region
+    const bool shrink = e ? atoi(e) != 0 : (top.flags & B200BKZ_SHRINK_RADIUS) != 0;
+    enum_flags        = shrink ? 0 : B200ENUM_FIXED_RADIUS;
   }
+  int enum_flags = 0;
 
   // ---- thin wrappers over the device GSO -------------------------------------------------------------
   void lll(int kmin, int kstart, int kend, long *n_swaps)
@@ -392,7 +396,7 @@ public:
       std::vector<uint64_t> nodes(block_size);
       const double t0 = now_s();
       const int rc    = b200enum_run(block_size, maxdist_norm, mut.data(), rdiag.data(),
-                                     pr->coeff.empty() ? nullptr : pr->coeff.data(), 0, ctx->devs.data(),
+                                     pr->coeff.empty() ? nullptr : pr->coeff.data(), enum_flags, ctx->devs.data(),
                                      (int)ctx->devs.size(), 0, 1, sol_cb, &sc, nodes.data(), &es);
       st->sec_enum += now_s() - t0;
       st->enum_calls++;

@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(XS ? THREADS_XS : THREADS) k_enum(EnumArgs a)
           my_leaves++;
           const unsigned long long nb  = (unsigned long long)__double_as_longlong(newdist);
           const unsigned long long old = atomicMin(a.words + (a.fixed_radius ? W_BEST : W_A), nb);
-          if (nb < old)
+          // (fixed radius: ties with the best so far are recorded too — the host picks among equally short vectors by
+          // their coefficients, so the result does not depend on which walker got there first)
+          if (nb < old || (a.fixed_radius && nb == old))
           {
             const unsigned slot = atomicAdd(sol_count, 1u);
             if (slot < SOL_CAP)
@@ -703,6 +705,7 @@ struct Tuning
   unsigned long long fan_nodes;
   int min_roots;
   unsigned yield_small;
+  int shard_roots;
   const char *trace;
 };
 const Tuning &tuning()
@@ -722,6 +725,7 @@ const Tuning &tuning()
     // handful ever get there, so a tour never pays for devices it cannot use.
     q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 32000000);
     q.min_roots   = (int)geti("B200_ENUM_MIN_ROOTS", MIN_ROOTS);
+    q.shard_roots = (int)geti("B200_ENUM_SHARD_ROOTS", 8192);
     // rounds with fewer tasks than warps are bound by the latency of a lone walker (~0.35 us per node): yield sooner
     q.yield_small = (unsigned)geti("B200_ENUM_YIELD_SMALL", 8);  // BKZ-60 tour: 4.9 s -> 3.5 s of enumeration (gpurun_out/r2)
     q.trace     = getenv("B200_ENUM_TRACE");  // append one line per call to this file
@@ -827,7 +831,12 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
 
   // ---- host breadth phase ----
   Breadth br;
-  const size_t want = (size_t)tn.min_roots * (size_t)shard_world;
+  // A sharded call (one process per GPU) shares only its ROOTS between the ranks — the tasks a walker splits off later
+  // stay in its own device's queue — so the roots must be fine-grained enough to balance a heavy-tailed tree on their
+  // own: with 128 roots per rank two B200 finished the 5.6e8-node BKZ-60 block no sooner than one (profiles/r2_mgpu.txt).
+  size_t want = (size_t)tn.min_roots * (size_t)shard_world;
+  if (shard_world > 1)
+    want = std::max(want, (size_t)tn.shard_roots);
   breadth_phase(d, mut, rdiag, prun.data(), maxdist, dual, std::min<size_t>(want, MAX_ROOTS), MAX_ROOTS, br);
   const int T = (int)br.lev.size(), L = d - T;
   const std::vector<BNode> &leaf = br.lev[T - 1];
@@ -1186,7 +1195,13 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
   {
     if (!found.empty())
     {
-      deliver(found.back());
+      // the shortest vector inside the fixed region; among equally short ones the lexicographically smallest coefficient
+      // vector — a function of the input alone, whatever the schedule of the walkers and the number of devices was
+      const SolRec *best = &found.back();
+      for (const SolRec &s : found)
+        if (s.dist == best->dist && std::lexicographical_compare(s.x, s.x + d, best->x, best->x + d))
+          best = &s;
+      deliver(*best);
       nrep = 1;
     }
   }

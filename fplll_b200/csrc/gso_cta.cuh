@@ -32,6 +32,9 @@
 #ifndef B200_CTA_MOVE
 #define B200_CTA_MOVE 1
 #endif
+#ifndef B200_PUB_SLEEP
+#define B200_PUB_SLEEP 0  // nanoseconds a consumer of a streamed wavefront sleeps between two polls of a slot (0: spin)
+#endif
 
 namespace b200 {
 
@@ -118,10 +121,17 @@ __device__ inline double pub_wait(const double *slot, double tag)
 {
   double val, t;
   const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
-  do
+  for (;;)
   {
     asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(val), "=d"(t) : "r"(a) : "memory");
-  } while (t != tag);
+    if (t == tag)
+      break;
+#if B200_PUB_SLEEP
+    // back off: up to seven warps poll slots of the same panel while its owner's own shared-memory traffic (tile entries,
+    // the published values) has to get through the same load/store queue
+    __nanosleep(B200_PUB_SLEEP);
+#endif
+  }
   return val;
 }
 

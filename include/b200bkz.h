@@ -25,6 +25,13 @@ typedef struct b200bkz b200bkz_t;
 #define B200BKZ_BOUNDED_LLL 0x10
 #define B200BKZ_AUTO_ABORT 0x20
 #define B200BKZ_GH_BND 0x80
+/* Not a reference flag.  By default every SVP call enumerates the FIXED region of its initial radius and pruning bounds and
+ * takes the shortest vector inside it (ties: smallest coefficient vector): a function of the block alone, so a tour is
+ * reproducible run to run and across device counts, and never worse than what the reference's walk returns.  With this
+ * flag the radius shrinks the moment a walker meets an admissible vector, like the reference's evaluator
+ * (enum/evaluator.h:122-156): fewer nodes, but which vector is met first — hence the whole trajectory of a pruned tour —
+ * depends on the schedule of thousands of walkers (the reference has the same property with set_threads > 1). */
+#define B200BKZ_SHRINK_RADIUS 0x10000
 
 /* RedStatus values this driver can return (defs.h:153-169) */
 #define B200_RED_BKZ_FAILURE 6
