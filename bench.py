@@ -444,8 +444,8 @@ def main():
     if dist and not a.no_extras:
         try:
             from fplll_b200.dist import enumerate_svp_distributed, attach_peers
-            # once per job: the ranks' enumerators reach each other's radius word and rank 0's subtree ticket over
-            # NVLink (CUDA IPC handles all-gathered with NCCL) — shared ticket + radius push inside the kernel
+            # once per job: the ranks' enumerators reach each other's radius words over NVLink (CUDA IPC handles
+            # all-gathered with NCCL) — radius push inside the kernel; the subtree roots are dealt round-robin
             peers = attach_peers(device_index=local)
             z = np.load(os.path.join(ROOT, "tests", "golden", "enum_r200_b60_pruned_140.npz"))
             enumerate_svp_distributed(z["mut"], z["rdiag"], z["pruning"], float(z["maxdist"]), device_index=local)
@@ -457,9 +457,9 @@ def main():
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             n = int(res["nodes"].sum())
-            enum_dist = {"workload": "SVP enumeration of a BKZ-60 block of the dim-200 basis, subtree roots claimed by "
-                                     "%d ranks from one ticket in rank 0's memory (NVLink peer atomics), radius pushed to "
-                                     "all peers, results merged with NCCL" % world, "peer_memory": bool(peers), "nodes": n,
+            enum_dist = {"workload": "SVP enumeration of a BKZ-60 block of the dim-200 basis, 8192 subtree roots dealt over "
+                                     "%d ranks in order of promise, radius pushed to all peers (NVLink peer atomics over "
+                                     "CUDA IPC), results merged with NCCL" % world, "peer_memory": bool(peers), "nodes": n,
                          "nodes_equal_reference": n == int(z["nodes"].sum()), "seconds_max_over_ranks": float(dt[0]),
                          "nodes_per_s": n / float(dt[0])}
         except Exception as ex:

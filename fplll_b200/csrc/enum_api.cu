@@ -22,8 +22,9 @@
 //      call that is still busy after `fan_nodes` nodes SUSPENDS at a round boundary; its pending task queue is copied to
 //      every other device over NVLink (cudaMemcpyPeer) and all devices — the first one included — resume from it,
 //      claiming tasks from ONE shared ticket in device 0's memory (system-scope atomicAdd), the device-side form of
-//      enumlib's shared subtree counter (enumeration.h:460-475).  One-process-per-GPU jobs start directly in that mode on
-//      the host's subtree roots, ticket and radius words reached through CUDA IPC (b200enum_ipc_*).
+//      enumlib's shared subtree counter (enumeration.h:460-475).  One-process-per-GPU jobs (sharded calls) deal the host's
+//      subtree roots round-robin in order of promise — 8192 roots, so the deal balances a heavy-tailed tree — and push
+//      radius improvements into each other's words, reached through CUDA IPC (b200enum_ipc_*).
 // Arithmetic: every centre is the chain ((0 - x[d-1] mu) - x[d-2] mu) - ... in descending j with separately rounded
 // multiply and subtract (--fmad=false), the order of the reference's center_partsums, so with a fixed radius the set
 // of visited nodes — and therefore the node count — is identical to the reference's own enumerator.
@@ -154,24 +155,6 @@ __device__ inline unsigned long long atomic_add_sys(unsigned long long *p, unsig
   unsigned long long old;
   asm volatile("atom.global.sys.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
   return old;
-}
-
-// One thread installs the call's epoch in the shared ticket (count 0) unless a peer already did: the ticket is never
-// reset by its owner, so no rank has to wait for another one before it starts claiming (all ranks of call e-1 are done
-// before any rank starts call e — they exchanged results in between).
-__global__ void k_epoch(unsigned long long *gticket, unsigned epoch)
-{
-  for (;;)
-  {
-    unsigned long long cur = *(volatile unsigned long long *)gticket;
-    if ((unsigned)(cur >> 32) == epoch)
-      return;
-    unsigned long long seen;
-    const unsigned long long want = (unsigned long long)epoch << 32;
-    asm volatile("atom.global.sys.cas.b64 %0, [%1], %2, %3;" : "=l"(seen) : "l"(gticket), "l"(cur), "l"(want) : "memory");
-    if (seen == cur)
-      return;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -720,10 +703,11 @@ const Tuning &tuning()
     q.use_xs         = (int)geti("B200_ENUM_XS", 1);
     q.xs_threads_cap = (int)geti("B200_ENUM_XS_THREADS", 320);
     // hand-off threshold: a call that has visited this many nodes on the first device and still has work pending is
-    // spread over all devices.  32 M nodes = ~4 ms of one B200 against ~0.5 ms for the hand-off (peer copies, one
-    // cooperative launch and one read-back per device): of the ~18 k enumerations of a BKZ-60 tour on dim 200 only a
-    // handful ever get there, so a tour never pays for devices it cannot use.
-    q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 32000000);
+    // spread over all devices.  200 M nodes = ~25 ms of one B200.  With 32 M the BKZ-60 tour on two devices spent 7.0 s
+    // in enumeration against 4.5 s on one (fixed-region calls of 30-100 M nodes are common, and suspending at a round
+    // boundary + peer copies + a cooperative launch and a read-back per device cost more than half such a call saves):
+    // a tour must never pay for devices it cannot use.
+    q.fan_nodes = (unsigned long long)geti("B200_ENUM_FAN_NODES", 200000000);
     q.min_roots   = (int)geti("B200_ENUM_MIN_ROOTS", MIN_ROOTS);
     q.shard_roots = (int)geti("B200_ENUM_SHARD_ROOTS", 8192);
     // rounds with fewer tasks than warps are bound by the latency of a lone walker (~0.35 us per node): yield sooner
@@ -849,16 +833,22 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
   const auto t_host = std::chrono::steady_clock::now();
 
   // ---- contexts ----
-  std::vector<DevCtx *> ctxs(ndev);
-  for (int q = 0; q < ndev; q++)
-  {
+  // Only the first device is touched here: the others are set up when (and if) a call is handed off to them — a BKZ tour
+  // issues ~18 k calls of which a handful fan out, and two cudaSetDevice round trips per call were 0.6 s of a tour.
+  std::vector<DevCtx *> ctxs(ndev, nullptr);
+  auto prepare_ctx = [&](int q) -> int {
+    if (ctxs[q])
+      return 0;
     int rc = get_ctx(devices[q], &ctxs[q]);
     if (rc)
       return rc;
     CKE(cudaSetDevice(ctxs[q]->device));
     // sized for dim <= 64 up front (BKZ calls with every block size from 2 to beta: growing would re-allocate ~1 GB
     // a dozen times), re-allocated once if a larger dimension ever shows up
-    rc = ensure(&ctxs[q]->d_tx, &ctxs[q]->tx_cap, (size_t)2 * TASK_CAP * (d <= 64 ? 64 : B200ENUM_MAX_DIM));
+    return ensure(&ctxs[q]->d_tx, &ctxs[q]->tx_cap, (size_t)2 * TASK_CAP * (d <= 64 ? 64 : B200ENUM_MAX_DIM));
+  };
+  {
+    const int rc = prepare_ctx(0);
     if (rc)
       return rc;
   }
@@ -866,11 +856,14 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
   const int dstride = (d + 3) & ~3;
   const size_t cfg_n = (size_t)d * d + 2 * d;
   const size_t off_cfg = DevCtx::OFF_STAGE, off_hdr = off_cfg + ((cfg_n * 8 + 15) & ~(size_t)15);
-  // ipc mode: ranks attached to each other share rank 0's ticket and push radii; otherwise the roots are dealt statically
+  // ipc mode: ranks attached to each other push radius improvements into each other's words over NVLink.  The roots are
+  // dealt round-robin in order of promise in either case: a shared ticket over the ROOTS was measured and dropped — a root
+  // is split into its device's own queue after 64 nodes, so the 47 k walkers of whichever rank starts a few microseconds
+  // earlier claim every root before the other one arrives (2 ranks: 0.074 s against 0.071 s for one, profiles/r2_mgpu.txt).
   const bool ipc = shard_world > 1 && home->ipc_world == shard_world && home->ipc_rank == shard_rank;
-  // the staged round-0 tasks of this process: all roots (shared ticket) or its static share
+  // the staged round-0 tasks of this process: its share of the roots
   std::vector<unsigned> mine;
-  if (shard_world > 1 && !ipc)
+  if (shard_world > 1)
     for (size_t g = (size_t)shard_rank; g < nroots; g += (size_t)shard_world)
       mine.push_back(order[g]);
   else
@@ -957,32 +950,17 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
 
   // ---- phase A: the first device ----
   CKE(cudaSetDevice(home->device));
-  if (ipc)
-  {
-    // every word but the shared ticket: a peer that starts this call earlier may already be claiming from it (its owner
-    // never resets it — k_epoch below installs the call's epoch on whichever rank gets there first)
-    const size_t tk = DevCtx::OFF_WORDS + (size_t)W_GTICKET * 8;
-    CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, tk - DevCtx::OFF_WORDS,
-                        cudaMemcpyHostToDevice, home->stream));
-    CKE(cudaMemcpyAsync(home->d_blk + tk + 8, home->h_up + tk + 8, up_end - tk - 8, cudaMemcpyHostToDevice, home->stream));
-  }
-  else
-    CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, up_end - DevCtx::OFF_WORDS,
-                        cudaMemcpyHostToDevice, home->stream));
+  CKE(cudaMemcpyAsync(home->d_blk + DevCtx::OFF_WORDS, home->h_up + DevCtx::OFF_WORDS, up_end - DevCtx::OFF_WORDS,
+                      cudaMemcpyHostToDevice, home->stream));
   CKE(cudaEventRecord(home->e0, home->stream));
   EnumArgs a0;
   make_args(home, a0);
   a0.hdr_first = (const TaskHdr *)(home->d_blk + off_hdr), a0.tx_first = (const int *)(home->d_blk + off_tx);
   a0.out0 = 0, a0.n_first = (unsigned)nmine;
   if (ipc)
-  {
-    home->epoch++;
-    a0.gticket = home->ipc_words[0] + W_GTICKET, a0.gepoch = home->epoch, a0.share_div = shard_world;
     for (int r = 0; r < shard_world; r++)
       if (r != shard_rank)
         a0.A_peer[a0.n_peer++] = home->ipc_words[r] + W_A;
-    k_epoch<<<1, 1, 0, home->stream>>>(a0.gticket, a0.gepoch);
-  }
   a0.node_cap = (ndev > 1) ? tn.fan_nodes : 0;
   bool fanned = false;
   if (nmine > 0)
@@ -1012,6 +990,12 @@ int run_impl(int dim, double maxdist, const double *mut_in, const double *rdiag_
     {
       fanned = true;
       used_dev = ndev;
+      for (int q = 1; q < ndev; q++)
+      {
+        rc = prepare_ctx(q);
+        if (rc)
+          return rc;
+      }
       rc = enable_peers(ctxs);
       if (rc)
         return rc;

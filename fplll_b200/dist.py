@@ -37,9 +37,9 @@ _attached = {}
 
 
 def attach_peers(group=None, device_index=0):
-    """Once per job: let the ranks' enumerators reach each other's radius word and rank 0's subtree ticket over NVLink
-    (CUDA IPC; include/b200enum.h b200enum_ipc_*).  The 64-byte handles are all-gathered through the process group
-    (NCCL on GPUs).  Without it sharded calls fall back to a static deal of the roots with private radii."""
+    """Once per job: let the ranks' enumerators reach each other's radius words over NVLink (CUDA IPC; include/b200enum.h
+    b200enum_ipc_*).  The 64-byte handles are all-gathered through the process group (NCCL on GPUs).  Without it sharded
+    calls run with private radii."""
     from . import enumeration as en
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     key = (id(group), device_index)
@@ -57,9 +57,10 @@ def attach_peers(group=None, device_index=0):
 
 
 def enumerate_svp_distributed(mut, rdiag, pruning, maxdist, group=None, device_index=0, fixed_radius=False):
-    """sharded enumeration across the ranks of `group` (one GPU per rank).  After attach_peers() the ranks claim subtree
-    roots from one shared ticket and push radius improvements to each other inside the kernel (NVLink peer memory);
-    the result merge below (NCCL) is also what keeps call k+1 from starting before every rank finished call k."""
+    """sharded enumeration across the ranks of `group` (one GPU per rank): the subtree roots are dealt round-robin in
+    order of promise; after attach_peers() the ranks push radius improvements to each other inside the kernel (NVLink
+    peer memory).  The result merge below (NCCL) is also what keeps call k+1 from starting before every rank finished
+    call k."""
     from . import enumeration as en
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = en.enumerate_svp(mut, rdiag, pruning, maxdist, fixed_radius=fixed_radius, devices=[device_index],

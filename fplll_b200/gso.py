@@ -106,7 +106,7 @@ class MatGSO:
         return ok.astype(bool)
 
     def update_gso_blocked(self, gram_mode=0):
-        """EXPERIMENTAL: update_gso() with the Gram matrix recomputed in 32x32 tiles first (0: reference-order dot
+        """update_gso() with the Gram matrix recomputed in 32x32 tiles first (0: reference-order dot
         products, 1: fp64 tensor-core DMMA) — include/b200gso.h."""
         ok = np.zeros(self.batch, np.int32)
         _ck(_lib().b200gso_update_gso_blocked(self._h, gram_mode, _ptr(ok, C.c_int)), "update_gso_blocked")

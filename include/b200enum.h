@@ -84,12 +84,12 @@ int b200enum_run_ex(int dim, double maxdist, const double *mut, const double *rd
                     const int *devices, int ndev, int shard_rank, int shard_world, b200enum_sol_cb cb,
                     b200enum_subsol_cb subcb, void *ctx, uint64_t *nodes, b200enum_stats *stats);
 
-/* One process per GPU (torch.distributed): let the ranks' enumerators reach each other's radius word and rank 0's
- * subtree ticket over NVLink (CUDA IPC).  Every rank exports a handle for its device, the job all-gathers the
- * world*64 bytes (NCCL / gloo), every rank attaches.  After that, sharded calls (shard_world == world) claim subtree
- * roots from ONE ticket and push every radius improvement to all peers — enumlib's shared counter and shared radius
- * (enum-parallel/enumeration.h:62-81,460-475) — instead of a static deal with private radii.  Ranks must not start
- * call k+1 before every rank has finished call k (the result exchange after each call guarantees that). */
+/* One process per GPU (torch.distributed): let the ranks' enumerators reach each other's radius words over NVLink (CUDA
+ * IPC).  Every rank exports a handle for its device, the job all-gathers the world*64 bytes (NCCL / gloo), every rank
+ * attaches.  After that, sharded calls (shard_world == world) push every radius improvement to all peers — enumlib's
+ * one shared radius (enum-parallel/enumeration.h:62-81) — instead of running with private radii; the subtree roots are
+ * dealt round-robin in order of promise either way.  Ranks must not start call k+1 before every rank has finished call
+ * k (the result exchange after each call guarantees that). */
 int b200enum_ipc_export(int device, unsigned char *handle64);
 int b200enum_ipc_attach(int device, int world, int rank, const unsigned char *handles);
 int b200enum_ipc_detach(int device);

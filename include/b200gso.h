@@ -78,9 +78,9 @@ int b200gso_discover_rows(b200gso_t *h, int upto);
 int b200gso_update_gso_row(b200gso_t *h, int i, int last_j, int *ok);
 /* MatGSOInterface::update_gso, gso_interface.h:767-775 */
 int b200gso_update_gso(b200gso_t *h, int *ok);
-/* EXPERIMENTAL (written at the end of round 1, not yet run on hardware; nothing else calls it): update_gso() with the
- * whole float Gram matrix recomputed first in 32 x 32 tiles — the blocked form of get_gram (gso.h:314-331) — then the
- * row sweeps.  B200GSO_GRAM_ORDERED keeps the reference's left-to-right dot products (bit-identical state);
+/* update_gso() with the whole float Gram matrix recomputed first in 32 x 32 tiles — the blocked form of get_gram
+ * (gso.h:314-331) — then the row sweeps (validated on hardware in round 2: bit-exact / within 1e-9, 2-3x the row-by-row
+ * form, profiles/r2_validation_queue.txt).  B200GSO_GRAM_ORDERED keeps the reference's left-to-right dot products (bit-identical state);
  * B200GSO_GRAM_DMMA uses fp64 tensor-core mma.m8n8k4 (identical only where every partial sum is exact). */
 #define B200GSO_GRAM_ORDERED 0
 #define B200GSO_GRAM_DMMA 1

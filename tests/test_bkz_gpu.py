@@ -120,3 +120,23 @@ def test_bkz60_default_strategies_on_dim200_one_tour_quality(fb):
     # the output is still a basis of the same lattice: the Gram determinant (sum of log r_ii, ~4400 here) is unchanged up
     # to what an fp64 GSO of a dim-200 basis can resolve (its tail r_ii carry ~1e-4 relative error)
     assert abs(np.log(gso_profile(b)).sum() - np.log(gso_profile(g["b"])).sum()) < 1.0
+
+
+def test_default_tours_are_reproducible_and_the_shrinking_radius_is_a_flag(fb):
+    """include/b200bkz.h: by default every SVP call enumerates the fixed region of its initial radius, so two runs of a
+    pruned, rerandomising BKZ with the same seed end on the same basis, bit for bit; B200BKZ_SHRINK_RADIUS (the
+    reference's order-dependent evaluator behaviour) is accepted and reduces as well."""
+    z = H.gold("bkz_q60.npz")
+    outs = []
+    for _ in range(2):
+        b = z["b_in"].copy()
+        st, stats = fb.bkz_reduction(b, fb.BKZParam(30, strategies="default", flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS,
+                                                    max_loops=2, seed=5))
+        assert st == 8
+        outs.append((b, int(stats["enum_nodes"]), int(stats["enum_calls"])))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
+    b = z["b_in"].copy()
+    st, stats = fb.bkz_reduction(b, fb.BKZParam(30, strategies="default", max_loops=2, seed=5,
+                                                flags=fb.BKZ_NO_LLL | fb.BKZ_MAX_LOOPS | fb.BKZ_SHRINK_RADIUS))
+    assert st == 8 and int(stats["enum_nodes"]) <= outs[0][1]
+    assert gso_profile(b)[0] <= gso_profile(z["b_in"])[0]

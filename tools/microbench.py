@@ -69,7 +69,7 @@ def main():
         out["M2"].append(rec)
         print("M2", json.dumps(rec), flush=True)
         m.close()
-        if os.environ.get("B200_TEST_EXPERIMENTAL"):  # blocked Gram (gso_gram.cuh): 0 = ordered, 1 = DMMA
+        if True:  # blocked Gram (gso_gram.cuh): 0 = ordered, 1 = DMMA
             for mode in (0, 1):
                 m = MatGSO(rand_basis(rng, B, d, n), GSO_ROW_EXPO)
                 m.sync()
