@@ -232,7 +232,7 @@ def hh_extras(local):
         from fplll_b200.householder import MatHouseholder
         d = n = 400
         i = d - 1
-        B = 2960  # = the resident warps of hk_update_R<14> on 148 SMs (one full wave)
+        B = int(os.environ.get("B200_BENCH_HH_BATCH", 2960))  # 2960 = the resident warps of hk_update_R<14> on 148 SMs
         rng = np.random.default_rng(7)
         b = rng.integers(-(1 << 20), 1 << 20, size=(1, d, n), dtype=np.int64)
         m = MatHouseholder(np.broadcast_to(b, (B, d, n)), 5, device=local, keep_history=False)

@@ -737,7 +737,6 @@ __global__ void hk_set_updated(HBatch S, int val)
 // sweep over k (the dot product of j+1 only needs R[k] after the update of j at the same k), so V is streamed once from
 // HBM and once more from L2, and every element costs one dependent DADD (8 cycles) instead of two passes.
 // Operation order per lattice is exactly w_update_R's (householder.cpp:151-184): bit-identical R.
-constexpr int X_STAGES  = 8;
 constexpr int X_K       = 16;                 // elements of a row per chunk
 constexpr int X_HALF_DBL = 32 * X_K;          // one box: 32 lattices x 16 doubles (4 KB)
 constexpr int X_STAGE_DBL = 2 * X_HALF_DBL;   // A (V_j) + B (V_{j+1})
@@ -761,6 +760,19 @@ __device__ inline void x_mbar_wait(unsigned long long *bar, unsigned parity)
                "r"(parity)
                : "memory");
 }
+__device__ inline bool x_mbar_test(unsigned long long *bar, unsigned parity)
+{
+  unsigned ok;
+  asm volatile("{\n\t"
+               ".reg .pred p;\n\t"
+               "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t"
+               "}"
+               : "=r"(ok)
+               : "r"(x_smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
 __device__ inline void x_tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
 {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
@@ -769,27 +781,8 @@ __device__ inline void x_tma_2d(void *dst, const CUtensorMap *map, int c0, int c
                : "memory");
 }
 
-// the chunk sequence: pass -2 loads R_i; pass j = -1 .. i-1 sweeps k from (max(j,0) & ~15) to n in steps of 16 with
-// A = V_j (j >= 0) and B = V_{j+1} (j + 1 < i)
-struct XIter
-{
-  int j, k0;
-  __device__ void start() { j = -2, k0 = 0; }
-  __device__ bool done(int i) const { return j >= i; }
-  __device__ void next(int n, int i)
-  {
-    k0 += X_K;
-    if (k0 >= n)
-    {
-      j++;
-      if (j == -1 && i < 1)
-        j = 0;  // no reflections at all: nothing after the load
-      k0 = max(j, 0) & ~(X_K - 1);
-    }
-  }
-};
-
-// lane r's 16 elements of a swizzled box: element k at row r, 16-byte column (k >> 1) ^ (r & 7)
+// lane r's 16 elements of a swizzled box: element k at row r, 16-byte column (k >> 1) ^ (r & 7).  (Dense 256-byte rows
+// read back with a per-lane skew were measured too — half the TMA row requests — and were slower: 2.47 against 1.77 ms.)
 __device__ inline void x_read_box(const double *box, int lane, double (&v)[X_K])
 {
   const char *row = (const char *)box + lane * 128;
@@ -801,141 +794,291 @@ __device__ inline void x_read_box(const double *box, int lane, double (&v)[X_K])
   }
 }
 
-__global__ void __launch_bounds__(32, 1) hk_update_R_x32(HBatch S, int i, const __grid_constant__ XMaps M)
+// ---- one CTA per group of 32 lattices = 1 producer warp + XM_NA update warps + 1 chain warp ----
+// A single warp doing the whole sweep is bound by its own issue rate (first version: one instruction every 3.7 cycles, 0.17
+// of the HBM peak, profiles/r2_hh_x32.txt).  Here the sweep over k of pass q (reflection j = q - 2) is a pipeline of three
+// roles connected by mbarriers:
+//   producer  lane 0 of warp 0 walks the chunk sequence and issues the TMA boxes of chunk g into stage g % XM_S as soon
+//             as the stage is empty;
+//   update    warp 1 + (g % XM_NA) takes chunk g: R[k] += V_j[k] * f_j (times sigma_j at k = j), writes R back to shared
+//             memory and the products  p[k] = V_{j+1}[k] * R[k]  into slot g % XM_PR of a product ring;
+//   chain     the last warp consumes the product slots IN ORDER and adds them — one dependent DADD per element, the only
+//             serial work left — and at the end of a pass publishes f_{j+1} = -sum for the update warps of the next pass.
+// Every lattice (lane) sees exactly w_update_R's operation order (householder.cpp:151-184): bit-identical R.
+constexpr int XM_NA = 6;   // update warps
+constexpr int XM_S  = 8;   // TMA stages (A | B boxes, 8 KB each)
+constexpr int XM_PR = 8;   // product slots (4 KB each)
+constexpr int XM_WARPS = XM_NA + 2;
+static_assert(XM_S == XM_PR, "an update warp relies on 'product slot free' implying 'TMA stage consumed'");
+
+struct XmCtl
+{
+  unsigned long long full[XM_S], empty[XM_S], pready[XM_PR], pfree[XM_PR];
+  // number of passes the chain warp has closed.  A plain counter, not an mbarrier: an update warp without a chunk in some
+  // passes (late passes have fewer chunks than there are update warps) would have to skip phases, and a parity wait can
+  // only tell adjacent phases apart.
+  int pass_done;
+  int pad;
+};
+__device__ inline void xm_store_release(int *p, int v)
+{
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(x_smem_u32(p)), "r"(v) : "memory");
+}
+__device__ inline int xm_load_acquire(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(x_smem_u32(p)) : "memory");
+  return v;
+}
+
+__device__ inline void xm_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(x_smem_u32(bar)) : "memory");
+}
+
+// chunk sequence in pass-major order: pass q = 0 loads R_i (k0 = 0, 16, ...); pass q >= 1 is reflection j = q - 2 (j = -1:
+// only the dot product of reflection 0), k0 from (max(j,0) & ~15) in steps of 16.  Passes 0 .. i + 1.
+struct XmIter
+{
+  int q, k0;
+  __device__ void start() { q = 0, k0 = 0; }
+  __device__ bool done(int i) const { return q > i + 1; }
+  __device__ bool last_of_pass(int n) const { return k0 + X_K >= n; }
+  __device__ void next(int n)
+  {
+    k0 += X_K;
+    if (k0 >= n)
+    {
+      q++;
+      k0 = max(q - 2, 0) & ~(X_K - 1);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(XM_WARPS * 32, 1) hk_update_R_x32(HBatch S, int i, const __grid_constant__ XMaps M)
 {
   extern __shared__ unsigned char x_raw[];
-  const int lane = threadIdx.x, n = S.n;
-  const int l0 = blockIdx.x * 32, l = l0 + lane;
-  double *ring = (double *)(((size_t)x_raw + 1023) & ~(size_t)1023);
-  double *Rk   = ring + (size_t)X_STAGES * X_STAGE_DBL;  // [k][lane]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, n = S.n;
+  const int l0 = blockIdx.x * 32, l = l0 + lane, lc = min(l, S.B - 1);
+  double *ring = (double *)(((size_t)x_raw + 1023) & ~(size_t)1023);   // XM_S stages of A | B boxes
+  double *prod = ring + (size_t)XM_S * X_STAGE_DBL;                    // XM_PR slots of [u][lane]
+  double *Rk   = prod + (size_t)XM_PR * X_HALF_DBL;                    // [k][lane]
   const int npad = (n + X_K - 1) & ~(X_K - 1);
-  unsigned long long *bars = (unsigned long long *)(Rk + (size_t)npad * 32);
-  if (lane == 0)
+  double *fbuf = Rk + (size_t)npad * 32;                               // [2][lane]
+  XmCtl *C     = (XmCtl *)(fbuf + 64);
+  unsigned *sigbits = (unsigned *)(C + 1);                             // [j]: bit l set <=> sigma_j of lattice l is -1
+  // sigma_j is a sign (householder.cpp:40: +-1.0): all reflections' signs of the 32 lattices fit 4 i bytes, so no pass
+  // waits on a global load for it
+  for (int j = w; j < i; j += XM_WARPS)
   {
-    for (int q = 0; q < X_STAGES; q++)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(bars + q)));
+    const unsigned neg = __ballot_sync(FULLM, S.sigma[(size_t)lc * S.d + j] < 0.0);
+    if (lane == 0)
+      sigbits[j] = neg;
+  }
+  if (threadIdx.x == 0)
+  {
+    for (int q = 0; q < XM_S; q++)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&C->full[q])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&C->empty[q])));
+    }
+    for (int q = 0; q < XM_PR; q++)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&C->pready[q])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&C->pfree[q])));
+    }
+    C->pass_done = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncwarp();
-  const bool live = l < S.B && !S.meta[(size_t)min(l, S.B - 1) * HM_STRIDE + HM_UPDATED];
-  const size_t dn = (size_t)S.d * n;
+  __syncthreads();
 
-  XIter prod, cons;
-  prod.start(), cons.start();
-  unsigned issued = 0, consumed = 0;
-  auto issue = [&]() {
-    if (prod.done(i))
-      return;
-    if (lane == 0)
-    {
-      double *dst             = ring + (size_t)(issued % X_STAGES) * X_STAGE_DBL;
-      unsigned long long *bar = bars + (issued % X_STAGES);
-      if (prod.j == -2)
-      {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)), "r"(X_HALF_DBL * 8) : "memory");
-        x_tma_2d(dst, &M.R, i * n + prod.k0, l0, bar);
-      }
-      else
-      {
-        const bool hasA = prod.j >= 0, hasB = prod.j + 1 < i;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)),
-                     "r"((int)(hasA + hasB) * X_HALF_DBL * 8)
-                     : "memory");
-        if (hasA)
-          x_tma_2d(dst, &M.V, prod.j * n + prod.k0, l0, bar);
-        if (hasB)
-          x_tma_2d(dst + X_HALF_DBL, &M.V, (prod.j + 1) * n + prod.k0, l0, bar);
-      }
-    }
-    issued++;
-    prod.next(n, i);
-  };
-  for (int q = 0; q < X_STAGES; q++)
-    issue();
-
-  double acc = 0.0, f0 = 0.0, sg = 1.0, sg_next = 1.0;
-  // sigma of reflection 0 (householder.cpp:176: R(i,j) *= sigma[j])
-  if (i > 0)
-    sg_next = S.sigma[(size_t)min(l, S.B - 1) * S.d];
-  while (!cons.done(i))
+  if (w == 0)
   {
-    const int j = cons.j, k0 = cons.k0;
-    x_mbar_wait(bars + (consumed % X_STAGES), (consumed / X_STAGES) & 1u);
-    const double *st = ring + (size_t)(consumed % X_STAGES) * X_STAGE_DBL;
-    if (j == -2)
+    // ---- producer: lane p < XM_S owns stage p and issues the chunks g = p, p + XM_S, ... (one thread walking the whole
+    // sequence needs ~500 cycles per chunk — address arithmetic and barrier operations of a lone thread — and starved the
+    // pipeline: 1.77 ms per group; eight lanes do it eight wide) ----
+    if (lane < XM_S)
     {
-      double a[X_K];
-      x_read_box(st, lane, a);
-#pragma unroll
-      for (int u = 0; u < X_K; u++)
-        Rk[(size_t)(k0 + u) * 32 + lane] = a[u];
-    }
-    else
-    {
-      const bool hasA = j >= 0, hasB = j + 1 < i;
-      if (k0 == (max(j, 0) & ~(X_K - 1)))
+      XmIter it;
+      it.start();
+      for (int q = 0; q < lane && !it.done(i); q++)
+        it.next(n);
+      unsigned g  = lane;
+      bool active = !it.done(i);
+      while (__any_sync((1u << XM_S) - 1u, active))
       {
-        // first chunk of the pass: the factor of reflection j is the dot product the previous pass accumulated
-        f0 = -acc;
-        sg = sg_next;
-        if (j + 1 < i)
-          sg_next = S.sigma[(size_t)min(l, S.B - 1) * S.d + j + 1];
-      }
-      double a[X_K], b[X_K];
-      if (hasA)
-        x_read_box(st, lane, a);
-      if (hasB)
-        x_read_box(st + X_HALF_DBL, lane, b);
-      double *rp = Rk + (size_t)k0 * 32 + lane;
-      if (k0 > j + 1 && k0 + X_K <= n && hasA && hasB)
-      {
-        // interior chunk: every element takes the update of j and a term of the chain of j + 1
-        double r[X_K];
-#pragma unroll
-        for (int u = 0; u < X_K; u++)
-          r[u] = __dadd_rn(rp[u * 32], __dmul_rn(a[u], f0));
-#pragma unroll
-        for (int u = 0; u < X_K; u++)
-          rp[u * 32] = r[u];
-#pragma unroll
-        for (int u = 0; u < X_K; u++)
-          r[u] = __dmul_rn(b[u], r[u]);
-#pragma unroll
-        for (int u = 0; u < X_K; u++)
-          acc = __dadd_rn(acc, r[u]);
-      }
-      else
-      {
-#pragma unroll
-        for (int u = 0; u < X_K; u++)
+        if (active && x_mbar_test(&C->empty[lane], ((g / XM_S) & 1u) ^ 1u))
         {
-          const int k = k0 + u;
-          double r    = rp[u * 32];
-          if (hasA && k >= j && k < n)
+          double *dst             = ring + (size_t)lane * X_STAGE_DBL;
+          unsigned long long *bar = &C->full[lane];
+          const int j             = it.q - 2;
+          if (it.q == 0)
           {
-            r = __dadd_rn(r, __dmul_rn(a[u], f0));
-            if (k == j)
-              r = __dmul_rn(sg, r);
-            rp[u * 32] = r;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)), "r"(X_HALF_DBL * 8) : "memory");
+            x_tma_2d(dst, &M.R, i * n + it.k0, l0, bar);
           }
-          if (hasB && k >= j + 1 && k < n)
+          else
           {
-            const double t = __dmul_rn(b[u], r);
-            acc            = (k == j + 1) ? t : __dadd_rn(acc, t);
+            const bool hasA = j >= 0, hasB = j + 1 < i;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(bar)),
+                         "r"((int)(hasA + hasB) * X_HALF_DBL * 8)
+                         : "memory");
+            if (hasA)
+              x_tma_2d(dst, &M.V, j * n + it.k0, l0, bar);
+            if (hasB)
+              x_tma_2d(dst + X_HALF_DBL, &M.V, (j + 1) * n + it.k0, l0, bar);
           }
+          for (int q = 0; q < XM_S && !it.done(i); q++)
+            it.next(n);
+          g += XM_S;
+          active = !it.done(i);
         }
       }
     }
-    __syncwarp();
-    consumed++;
-    issue();
-    cons.next(n, i);
   }
+  else if (w <= XM_NA)
+  {
+    // ---- update warps ----
+    const int me = w - 1;
+    XmIter it;
+    it.start();
+    unsigned g = 0;
+    int fq = 0;          // passes up to fq have had their f / their predecessor's completion observed
+    double f0 = 0.0, sg = 1.0;
+    for (; !it.done(i); g++, it.next(n))
+    {
+      if ((int)(g % XM_NA) != me)
+        continue;
+      const int q = it.q, j = q - 2, k0 = it.k0;
+      if (q >= 1 && fq < q)
+      {
+        // pass q may start once the chain warp has closed pass q - 1: that orders every R[k] write of the earlier passes
+        // before this warp's reads, and carries f_j (j >= 0)
+        while (xm_load_acquire(&C->pass_done) < q)
+          ;
+        f0 = fbuf[(q & 1) * 32 + lane];
+        fq = q;
+        if (j >= 0)
+          sg = ((sigbits[j] >> lane) & 1u) ? -1.0 : 1.0;
+      }
+      // the product slot first: the chain warp consumes in order, so "slot g % 8 is free" also means chunk g - 8 — the
+      // previous user of this TMA stage — has landed and been consumed, and the parity wait below cannot see a stale phase
+      x_mbar_wait(&C->pfree[g % XM_PR], ((g / XM_PR) & 1u) ^ 1u);
+      x_mbar_wait(&C->full[g % XM_S], (g / XM_S) & 1u);
+      const double *st = ring + (size_t)(g % XM_S) * X_STAGE_DBL;
+      double *rp = Rk + (size_t)k0 * 32 + lane;
+      if (q == 0)
+      {
+        double a[X_K];
+        x_read_box(st, lane, a);
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          rp[u * 32] = a[u];
+      }
+      else
+      {
+        const bool hasA = j >= 0, hasB = j + 1 < i;
+        double a[X_K], b[X_K], r[X_K];
+        if (hasA)
+          x_read_box(st, lane, a);
+        if (hasB)
+          x_read_box(st + X_HALF_DBL, lane, b);
+        if (hasA && k0 > j && k0 + X_K <= n)
+        {
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+            r[u] = __dadd_rn(rp[u * 32], __dmul_rn(a[u], f0));
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+            rp[u * 32] = r[u];
+        }
+        else
+        {
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+          {
+            const int k = k0 + u;
+            double t    = rp[u * 32];
+            if (hasA && k >= j && k < n)
+            {
+              t = __dadd_rn(t, __dmul_rn(a[u], f0));
+              if (k == j)
+                t = __dmul_rn(sg, t);
+              rp[u * 32] = t;
+            }
+            r[u] = t;
+          }
+        }
+        if (hasB)
+        {
+          double *ps = prod + (size_t)(g % XM_PR) * X_HALF_DBL + lane;
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+            ps[u * 32] = __dmul_rn(b[u], r[u]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+        xm_arrive(&C->pready[g % XM_PR]);
+        xm_arrive(&C->empty[g % XM_S]);
+      }
+    }
+  }
+  else
+  {
+    // ---- chain warp ----
+    XmIter it;
+    it.start();
+    double acc = 0.0;
+    for (unsigned g = 0; !it.done(i); g++, it.next(n))
+    {
+      const int q = it.q, j = q - 2, k0 = it.k0;
+      x_mbar_wait(&C->pready[g % XM_PR], (g / XM_PR) & 1u);
+      if (q >= 1 && j + 1 < i)
+      {
+        const double *ps = prod + (size_t)(g % XM_PR) * X_HALF_DBL + lane;
+        double t[X_K];
+#pragma unroll
+        for (int u = 0; u < X_K; u++)
+          t[u] = ps[u * 32];
+        if (k0 > j + 1 && k0 + X_K <= n)
+        {
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+            acc = __dadd_rn(acc, t[u]);
+        }
+        else
+        {
+#pragma unroll
+          for (int u = 0; u < X_K; u++)
+          {
+            const int k = k0 + u;
+            if (k >= j + 1 && k < n)
+              acc = (k == j + 1) ? t[u] : __dadd_rn(acc, t[u]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        xm_arrive(&C->pfree[g % XM_PR]);
+      if (it.last_of_pass(n))
+      {
+        // pass q is closed: f of reflection j + 1 (the factor of pass q + 1) is minus the dot product just accumulated
+        fbuf[((q + 1) & 1) * 32 + lane] = -acc;
+        __syncwarp();
+        if (lane == 0)
+          xm_store_release(&C->pass_done, q + 1);
+      }
+    }
+  }
+  __syncthreads();
+  const bool live = l < S.B && !S.meta[(size_t)lc * HM_STRIDE + HM_UPDATED];
   if (live)
   {
-    double *Rr = S.R + (size_t)l * dn + (size_t)i * n;
-    for (int k = 0; k < n; k++)
+    double *Rr = S.R + (size_t)l * S.d * n + (size_t)i * n;
+    for (int k = w; k < n; k += XM_WARPS)
       Rr[k] = Rk[(size_t)k * 32 + lane];
   }
 }
@@ -1011,17 +1154,16 @@ static void launch_update_R_h(b200hh *h, int i, int last_j)
 {
   const HBatch &S = h->S;
   // B200_HH_X32=1 selects the lane-per-lattice kernel (default: one warp per lattice).  It needs a batch (32 lattices per
-  // warp), no R_history (its scattered per-lattice writes would cost more than the V stream) and R_i of 32 lattices in
-  // shared memory — which caps it at ONE warp per SM at n = 400, and one warp issues an instruction every ~3.7 cycles:
-  // measured 0.171 of the HBM peak against 0.181 for hk_update_R on 4736 lattices (profiles/r2_hh_x32.txt), so it is
-  // kept as the tested starting point of the multi-warp form, not as the default.
+  // CTA), no R_history (its scattered per-lattice writes would cost more than the V stream) and R_i of 32 lattices in
+  // shared memory.  Measured 0.264 of the HBM peak against 0.181 for hk_update_R at one group per SM (4736 lattices) but
+  // 0.165 against 0.195 at 2960 (profiles/r2_hh_x32.txt: bound by the per-reflection hand-off), so it is not the default.
   const char *e     = getenv("B200_HH_X32");
   const int use_x32 = e ? atoi(e) : 0;
   const size_t npad = ((size_t)S.n + X_K - 1) & ~(size_t)(X_K - 1);
-  const size_t smx  = 1024 + (size_t)X_STAGES * X_STAGE_DBL * 8 + npad * 32 * 8 + X_STAGES * 8;
+  const size_t smx  = 1024 + ((size_t)XM_S * X_STAGE_DBL + (size_t)XM_PR * X_HALF_DBL + npad * 32 + 64) * 8 + sizeof(XmCtl) + (size_t)S.d * 4;
   if (use_x32 && S.B >= 64 && !S.keep_hist && i > 0 && smx <= 227 * 1024 && (size_t)S.d * S.n < (1ull << 31) && x_maps(h))
   {
-    hk_update_R_x32<<<(S.B + 31) / 32, 32, smx, h->stream>>>(S, i, h->xmaps);
+    hk_update_R_x32<<<(S.B + 31) / 32, XM_WARPS * 32, smx, h->stream>>>(S, i, h->xmaps);
     if (last_j)
       hk_update_R_last_cond<<<hgrid(h), HW * 32, h->smem, h->stream>>>(S, i);
     return;

@@ -259,8 +259,33 @@ def enum_dual_subsol_fixtures():
     np.savez_compressed(os.path.join(HERE, "enum_r200_b30_dual_subsols.npz"), **arrs)
 
 
+def config2_mpz_reference():
+    """BASELINE config #2 as written (LLL<mpz_t,double> on latticegen r 200 2000): the reference's own outcome — status,
+    GSO dump and basis of tests/shim_demo without the shim — as hashes in lll_r200_mpz_ref.json (33 s on one core)."""
+    import hashlib
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(HERE))
+    inp, out = os.path.join(TMP, "r200.txt"), os.path.join(TMP, "r200_out.bin")
+    open(inp, "w").write(O.latticegen(["r", 200, 2000]))
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "oracle", "_ref"))
+    env.pop("LD_PRELOAD", None)
+    p = subprocess.run([os.path.join(root, "tests", "_build", "shim_demo"), inp, "mpz", out], capture_output=True,
+                       text=True, env=env, timeout=900)
+    tok = dict(t.split("=") for t in p.stdout.split() if "=" in t)
+    sha = lambda f: hashlib.sha256(open(f, "rb").read()).hexdigest()
+    rec = dict(what="BASELINE config #2: reference LLLReduction<Z_NR<mpz_t>, FP_NR<double>> on latticegen r 200 2000",
+               made_by="tests/golden/make_golden.py::config2_mpz_reference",
+               input_md5=hashlib.md5(open(inp, "rb").read()).hexdigest(), status=int(tok["status"]),
+               gso_ok=int(tok["gso_ok"]), out_bin_sha256=sha(out), out_basis_sha256=sha(out + ".basis"))
+    json.dump(rec, open(os.path.join(HERE, "lll_r200_mpz_ref.json"), "w"), indent=2)
+    print(rec)
+
+
 if __name__ == "__main__":
-    if "--dual" in sys.argv:
+    if "--config2" in sys.argv:
+        config2_mpz_reference()
+    elif "--dual" in sys.argv:
         enum_dual_subsol_fixtures()
     elif "--configs" in sys.argv:
         config_size_fixtures()

@@ -65,6 +65,30 @@ def test_reference_lll_over_the_device_gso_is_byte_identical(tmp_path, mode):
     assert outs[0][0] == outs[1][0], "mu / r / row_expo differ"
 
 
+def test_config2_lll_on_r200_2000_in_the_mpz_regime_fails_exactly_like_the_reference(tmp_path):
+    """BASELINE config #2 at its stated size and in its stated regime: the reference's LLLReduction<Z_NR<mpz_t>,
+    FP_NR<double>> (GSO_ROW_EXPO | GSO_OP_FORCE_LONG, wrapper.cpp:538-553) on latticegen r 200 2000 — 2000-bit entries, B
+    stays in GMP on the host — with every update_gso_row forwarded to the device.  The reference's own fp64 stage cannot
+    finish this input (RED_BABAI_FAILURE near kappa = 180 after 33 s); the device GSO is bit-exact,
+    so the run must fail at the same point: same status, same mu / r / row_expo dump and same basis as the reference's
+    own run (tests/golden/lll_r200_mpz_ref.json, hashes)."""
+    import hashlib
+    import json
+    _need(SHIM, DEMO, os.path.join(REF, "libfplll.so"), os.path.join(REF, "latticegen"))
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lll_r200_mpz_ref.json")))
+    inp, out = str(tmp_path / "r200.txt"), str(tmp_path / "out.bin")
+    text = O.latticegen(["r", 200, 2000])
+    assert hashlib.md5(text.encode()).hexdigest() == ref["input_md5"]
+    open(inp, "w").write(text)
+    p = _run([DEMO, inp, "mpz", out], True, timeout=1500)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "status=%d gso_ok=%d" % (ref["status"], ref["gso_ok"]) in p.stdout and ref["status"] == 3, p.stdout
+    assert _stat(p.stdout, "adopted") >= 1 and _stat(p.stdout, "forwarded") > 100000, p.stdout
+    sha = lambda f: hashlib.sha256(open(f, "rb").read()).hexdigest()
+    assert sha(out + ".basis") == ref["out_basis_sha256"], "basis after the failing LLL differs"
+    assert sha(out) == ref["out_bin_sha256"], "mu / r / row_expo after the failing LLL differ"
+
+
 # the reference's test_bkz takes 4-5 minutes per run with every update_gso_row forwarded (260 s measured,
 # profiles/r2_shim_reference_tests.txt): deselected unless B200_TEST_SLOW=1 (tests/conftest.py)
 _SLOW = pytest.mark.slow
