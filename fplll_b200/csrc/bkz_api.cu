@@ -82,6 +82,8 @@ public:
     lll_delta = top.delta < 1 ? top.delta : 0.99;  // bkz.cpp:862
     const char *e = getenv("B200_BKZ_SHRINK");      // experiment knob: 1 forces the shrinking radius, 0 the fixed region
     const bool shrink = e ? atoi(e) != 0 : (top.flags & B200BKZ_SHRINK_RADIUS) != 0;
+    // (only pruned calls: without pruning the shrinking walk returns the shortest vector of the ball whatever the order,
+    // and the fixed ball would cost an unpruned BKZ-40 tour on dim 180 24 s instead of 1.7 s)
     enum_flags        = shrink ? 0 : B200ENUM_FIXED_RADIUS;
   }
   int enum_flags = 0;
@@ -396,7 +398,7 @@ public:
       std::vector<uint64_t> nodes(block_size);
       const double t0 = now_s();
       const int rc    = b200enum_run(block_size, maxdist_norm, mut.data(), rdiag.data(),
-                                     pr->coeff.empty() ? nullptr : pr->coeff.data(), enum_flags, ctx->devs.data(),
+                                     pr->coeff.empty() ? nullptr : pr->coeff.data(), pr->coeff.empty() ? 0 : enum_flags, ctx->devs.data(),
                                      (int)ctx->devs.size(), 0, 1, sol_cb, &sc, nodes.data(), &es);
       st->sec_enum += now_s() - t0;
       st->enum_calls++;

@@ -25,7 +25,7 @@ typedef struct b200bkz b200bkz_t;
 #define B200BKZ_BOUNDED_LLL 0x10
 #define B200BKZ_AUTO_ABORT 0x20
 #define B200BKZ_GH_BND 0x80
-/* Not a reference flag.  By default every SVP call enumerates the FIXED region of its initial radius and pruning bounds and
+/* Not a reference flag.  By default every PRUNED SVP call enumerates the FIXED region of its initial radius and pruning bounds and
  * takes the shortest vector inside it (ties: smallest coefficient vector): a function of the block alone, so a tour is
  * reproducible run to run and across device counts, and never worse than what the reference's walk returns.  With this
  * flag the radius shrinks the moment a walker meets an admissible vector, like the reference's evaluator
