@@ -22,7 +22,9 @@
 // mpz_get_d_2exp, stays on the host next to GMP).
 // An object is adopted the first time one of the first three functions sees it (constructors are inline in gso.h, but
 // they call size_increased(), which is how a new object at a recycled address is told from the old one); objects
-// the device cannot hold (GSO_INT_GRAM, MatGSOGram, d > 512) keep the reference's path untouched.  There is no CPU
+// the device cannot hold (MatGSOGram, d > 512) keep the reference's path untouched.  GSO_INT_GRAM objects (exact integer
+// Gram matrix, gso.cpp:140-159) are adopted too: b and g stay on the host, update_gso_row ships row i of g converted as
+// get_gram does (b200gso_set_gram_row) and the device does the forward substitution.  There is no CPU
 // fallback for an adopted object: a CUDA failure throws.
 //
 // On top of that, BKZReduction<Z_NR<long>, FP_NR<double>>::bkz() (bkz.cpp:522-672) — what bkz_reduction() / `fplll -a bkz`
@@ -58,11 +60,12 @@ struct Entry
   b200gso_t *h = nullptr;  // null: declined (the reference's path)
   int d = 0, n = 0;
   bool host_basis = false;
+  bool int_gram   = false;     // GSO_INT_GRAM object: the exact Gram matrix stays on the host, its rows travel as doubles
   int dev_nkr = 0;             // rows the device has discovered
   std::vector<int> dev_valid;  // the device's gso_valid_cols as of the last call (detects the inlined set_r)
   std::vector<double> row_mu, row_r;
   std::vector<int64_t> irow;
-  std::vector<double> frow;
+  std::vector<double> frow, frow_g;
 };
 
 static std::mutex g_mu;
@@ -211,13 +214,16 @@ template <class ZT> Entry *shim_entry(Guts<ZT> &g)
   }
   Entry e;
   auto *m = dynamic_cast<MatGSO<ZT, FP_NR<double>> *>(g.self);
-  bool ok = m != nullptr && !g.int_gram && g.d >= 1 && g.d <= 512 && b200gso_device_count() > 0;
+  bool ok = m != nullptr && g.d >= 1 && g.d <= 512 && b200gso_device_count() > 0;
   for (int i = 0; ok && i < g.nkr; i++)
     ok = g.valid[i] <= 0;  // adoption needs a GSO with nothing computed yet (true at the first update_gso_row / row_op_end)
   if (ok)
   {
     e.d = g.d, e.n = m->b.get_cols();
-    e.host_basis = B200ShimTraits<ZT>::host_basis;
+    // GSO_INT_GRAM (gso.cpp:140-159): b and the exact Gram matrix g stay on the host (row operations update g
+    // incrementally there); the device needs neither b nor bf, only the rows of g as doubles (b200gso_set_gram_row)
+    e.int_gram   = g.int_gram;
+    e.host_basis = B200ShimTraits<ZT>::host_basis || e.int_gram;
     const int flags = (g.row_expo_en ? B200GSO_ROW_EXPO : 0) | (e.host_basis ? B200GSO_HOST_BASIS : 0);
     if (b200gso_create(&e.h, 1, e.d, e.n, flags, 0) != 0)
       ok = false, e.h = nullptr;
@@ -229,8 +235,9 @@ template <class ZT> Entry *shim_entry(Guts<ZT> &g)
     return nullptr;
   }
   e.dev_valid.assign(e.d, 0);
-  e.row_mu.resize(e.d), e.row_r.resize(e.d), e.irow.resize(e.n), e.frow.resize(e.n);
-  shim_initial_basis(e, *m, g);  // the basis as the host has it now
+  e.row_mu.resize(e.d), e.row_r.resize(e.d), e.irow.resize(e.n), e.frow.resize(e.n), e.frow_g.resize(e.d);
+  if (!e.int_gram)
+    shim_initial_basis(e, *m, g);  // the basis as the host has it now
   b200shim::g_adopted++;
   Entry &slot = b200shim::g_tab[g.self] = e;
   return &slot;
@@ -258,6 +265,15 @@ template <class ZT> bool shim_update_gso_row(Guts<ZT> &g, Entry &e, int i, int l
       e.dev_valid[j] = j + 1;
       b200shim::g_setr++;
     }
+  if (e.int_gram)
+  {
+    // the Gram entries the update will read, exactly as the reference's get_gram converts them (gso.h:318-322)
+    const int cnt = std::min(i, last_j) + 1;
+    FP_NR<double> f;
+    for (int j = 0; j < cnt; j++)
+      e.frow_g[j] = g.self->get_gram(f, i, j).get_d();
+    b200shim::ck(b200gso_set_gram_row(e.h, i, cnt, e.frow_g.data()), "set_gram_row");
+  }
   int ok = 1;
   b200shim::ck(b200gso_update_gso_row(e.h, i, last_j, &ok), "update_gso_row");
   b200shim::g_updates++;
@@ -303,9 +319,12 @@ template <class ZT> bool shim_update_gso_row(Guts<ZT> &g, Entry &e, int i, int l
     if (!e)                                                                                                         \
       return;                                                                                                       \
     auto *m = static_cast<MatGSO<ZT, FP_NR<double>> *>(this);                                                       \
+    if (e->int_gram) /* nothing to ship (no bf): the device only invalidates; Gram rows travel with update_gso_row */    \
+      b200shim::ck(b200gso_row_op_end(e->h, first, last), "row_op_end");                                            \
     for (int i = first; i < last; i++) /* row i + row_op_end(i, i+1) on the device; the union is row_op_end(first, last) */ \
     {                                                                                                               \
-      shim_upload_row(*e, i, *m, g);                                                                                \
+      if (!e->int_gram)                                                                                             \
+        shim_upload_row(*e, i, *m, g);                                                                              \
       e->dev_valid[i] = 0;                                                                                          \
     }                                                                                                               \
     for (int i = last; i < d; i++)                                                                                  \

@@ -911,6 +911,29 @@ int b200gso_set_r(b200gso_t *h, int i, int j, const double *f)
   return 0;
 }
 
+// gf(i, 0..count-1) <- vals: the Gram row of a GSO_INT_GRAM object, computed exactly on the host (gso.h:314-331, int branch)
+__global__ void k_set_gram_row(Batch S, int i, int count, const double *vals)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S.B * count)
+    return;
+  const int l = t / count, j = t - l * count;
+  S.gf[(size_t)l * S.tri_stride + tri_off(i) + j] = vals[t];
+}
+
+int b200gso_set_gram_row(b200gso_t *h, int i, int count, const double *vals)
+{
+  if (!h || !vals || i < 0 || i >= h->S.d || count < 1 || count > i + 1)
+    return B200GSO_EINVAL;
+  CK(cudaSetDevice(h->device));
+  // staging: d_rowbuf holds 2 * batch * d doubles
+  CK(cudaMemcpyAsync(h->d_rowbuf, vals, sizeof(double) * (size_t)h->S.B * count, cudaMemcpyHostToDevice, h->stream));
+  k_set_gram_row<<<(h->S.B * count + 127) / 128, 128, 0, h->stream>>>(h->S, i, count, h->d_rowbuf);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int b200gso_get_state(b200gso_t *h, double *mu, double *r, double *gf, double *bf, int64_t *row_expo,
                       int *gso_valid_cols, int *init_row_size, int *meta)
 {

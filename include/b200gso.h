@@ -86,6 +86,13 @@ int b200gso_update_gso(b200gso_t *h, int *ok);
 #define B200GSO_GRAM_DMMA 1
 int b200gso_update_gso_blocked(b200gso_t *h, int gram_mode, int *ok);
 
+/* GSO_INT_GRAM objects (exact integer Gram matrix kept on the host, gso.cpp:140-159, gso_gram.cpp): get_gram(i, j) for
+ * j < count (gso.h:314-331, integer branch: the exact entry converted to double) written as row i of the float Gram
+ * matrix, so that the next update_gso_row(i, .) finds its Gram entries valid and only does the forward substitution.
+ * vals: batch * count doubles.  The handle is a B200GSO_HOST_BASIS one without row exponents (the reference forbids
+ * GSO_ROW_EXPO together with GSO_INT_GRAM, gso.h:116). */
+int b200gso_set_gram_row(b200gso_t *h, int i, int count, const double *vals);
+
 /* MatGSO::row_addmul_we(i, j, x, expo_add), gso.cpp:236-262: b_i += x * 2^expo_add * b_j with x an integer-valued
  * double converted by get_si_exp_we (nr_FP_d.inl:46-53).  x, expo_add: arrays of length batch. */
 int b200gso_row_addmul_we(b200gso_t *h, int i, int j, const double *x, const long *expo_add);

@@ -2,7 +2,7 @@
 // reference headers and linked with the unmodified libfplll.so.  Run once plainly and once with
 // LD_PRELOAD=libb200fplll.so (fplll_b200/csrc/fplll_matgso_shim.cpp): the second run executes every update_gso_row on
 // the B200 and must print byte-identical results (the device GSO is bit-exact, so LLL walks the same trajectory).
-// usage: shim_demo IN.txt long|mpz OUT.bin
+// usage: shim_demo IN.txt long|mpz|long_gram|mpz_gram OUT.bin     (_gram: GSO_INT_GRAM, the exact integer Gram matrix)
 #include <fplll/fplll.h>
 #include <cstdio>
 #include <fstream>
@@ -50,14 +50,16 @@ int main(int argc, char **argv)
   std::ifstream f(argv[1]);
   f >> B;
   const std::string mode = argv[2];
-  if (mode == "long")
+  if (mode == "long" || mode == "long_gram")
   {
     ZZ_mat<long> b(B.get_rows(), B.get_cols());
     for (int i = 0; i < B.get_rows(); i++)
       for (int j = 0; j < B.get_cols(); j++)
         b(i, j) = B(i, j).get_si();
-    run<long>(b, GSO_ROW_EXPO, argv[3]);
+    run<long>(b, mode == "long" ? GSO_ROW_EXPO : GSO_INT_GRAM, argv[3]);
   }
+  else if (mode == "mpz_gram")
+    run<mpz_t>(B, GSO_INT_GRAM, argv[3]);  // the flavour the wrapper's proved stage uses (wrapper.cpp:354-356)
   else
     run<mpz_t>(B, GSO_ROW_EXPO | GSO_OP_FORCE_LONG, argv[3]);  // wrapper.cpp:538-553
   long s[6] = {0, 0, 0, 0, 0, 0};

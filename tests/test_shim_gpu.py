@@ -38,16 +38,20 @@ def _stat(text, key):
     return int(text.split(key + "=")[1].split()[0])
 
 
-@pytest.mark.parametrize("mode", ["long", "mpz"])
+@pytest.mark.parametrize("mode", ["long", "mpz", "long_gram", "mpz_gram"])
 def test_reference_lll_over_the_device_gso_is_byte_identical(tmp_path, mode):
     """LLLReduction<ZT, FP_NR<double>>::lll() of the unmodified reference over its own MatGSO object, plain and with the
     shim preloaded: same status, same basis, same mu / r / row_expo bits; the preloaded run forwarded its updates.
     long: BASELINE config #1 (latticegen u 40 40-bit basis); mpz: a 400-bit knapsack basis that does not fit int64, the
-    regime where B stays in GMP on the host (GSO_ROW_EXPO | GSO_OP_FORCE_LONG, wrapper.cpp:538-553)."""
+    regime where B stays in GMP on the host (GSO_ROW_EXPO | GSO_OP_FORCE_LONG, wrapper.cpp:538-553); *_gram: the same two
+    integer types with GSO_INT_GRAM (the exact integer Gram matrix stays on the host, gso.cpp:140-159, its
+    rows travel as doubles through b200gso_set_gram_row)."""
     _need(SHIM, DEMO, os.path.join(REF, "libfplll.so"))
     inp = str(tmp_path / "in.txt")
     if mode == "long":
         O.write_matrix(inp, H.gold("u40_lll_long.npz")["b_in"])
+    elif mode == "long_gram":
+        open(inp, "w").write(O.latticegen(["u", 30, 12]))   # 12-bit entries: the exact Gram matrix fits Z_NR<long>
     else:
         open(inp, "w").write(O.latticegen(["r", 30, 400]))
     outs = []
@@ -59,7 +63,7 @@ def test_reference_lll_over_the_device_gso_is_byte_identical(tmp_path, mode):
         fwd = _stat(p.stdout, "forwarded")
         assert (fwd > 0) == preload, p.stdout
         if preload:
-            assert _stat(p.stdout, "adopted") >= 1 and _stat(p.stdout, "uploads") > 0
+            assert _stat(p.stdout, "adopted") >= 1 and (_stat(p.stdout, "uploads") > 0 or mode.endswith("_gram"))
         outs.append((open(out, "rb").read(), open(out + ".basis").read()))
     assert outs[0][1] == outs[1][1], "basis differs"
     assert outs[0][0] == outs[1][0], "mu / r / row_expo differ"
