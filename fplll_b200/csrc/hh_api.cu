@@ -810,6 +810,12 @@ constexpr int XM_S  = 8;   // TMA stages (A | B boxes, 8 KB each)
 constexpr int XM_PR = 8;   // product slots (4 KB each)
 constexpr int XM_WARPS = XM_NA + 2;
 static_assert(XM_S == XM_PR, "an update warp relies on 'product slot free' implying 'TMA stage consumed'");
+// ... and the product ring must not be shorter than the number of update warps: a warp's previous chunk is XM_NA behind
+// its current one, so with XM_PR >= XM_NA the chain warp is never two rounds of a slot behind a waiting warp — a parity
+// wait can only tell adjacent phases apart.  (XM_S = 13 / XM_PR = 4 — more bytes in flight, the measured bound of this
+// kernel: 64 KB per SM against ~2.8 us per box of 32 scattered 128-byte rows — passed the small parity tests and hung at
+// n = 400 for exactly this reason; growing the ring needs XM_NA <= XM_PR <= XM_S and the shared memory for it.)
+static_assert(XM_PR >= XM_NA, "product ring shorter than the number of update warps");
 
 struct XmCtl
 {
