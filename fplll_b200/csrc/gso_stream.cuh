@@ -153,7 +153,7 @@ __host__ __device__ inline int stream_num_chunks(const StreamShape &sh, int n)
     c += stream_panel_chunks(sh, p, n);
   return c;
 }
-__device__ inline StreamDesc stream_desc(const StreamShape &sh, int n, int ldb, int e)
+__host__ __device__ inline StreamDesc stream_desc(const StreamShape &sh, int n, int ldb, int e)
 {
   StreamDesc d;
   if (e == 0)
